@@ -1,0 +1,765 @@
+// tcgen05 / TMA / TMEM contractions for sm_100a.
+//
+//   dsvg_linear : Y[M,N] = epilogue(X[M,K] . W[N,K]^T)     both operands K-major   (forward + dgrad)
+//   dsvg_outer  : C[P,Q] += alpha * A[M,P]^T . B[M,Q]      both operands MN-major  (wgrad, contraction over rows)
+//
+// Both are warp-specialised: warp 0 = TMA producer (one elected lane), warp 1 = tcgen05.mma issuer (one lane) and
+// TMEM owner, warps 2..5 = epilogue (TMEM -> registers -> shared-memory transpose -> coalesced global accesses).
+// Operands land in shared memory through TMA with the 128-byte swizzle that the UMMA shared-memory descriptors
+// name; accumulators live in TMEM (fp32).  dsvg_linear is persistent (static round-robin tile schedule) with two
+// TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Parity mode ("bf16x3"): operands carry a second bf16 plane (lo = v - bf16(v)); the issuer runs three products
+// per K step (hi*hi + hi*lo + lo*hi) into the same accumulator.  Same kernel, NPLANES = 2.
+#include <cstdarg>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+
+#include "../../include/dsvg_b200.h"
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace dsvg {
+
+// ------------------------------------------------------------------------------------------------
+// error string + launch counter (shared by every translation unit)
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = {0};
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+unsigned long long g_launches = 0;
+static uint32_t g_outer_lbo = 0, g_outer_sbo = 0;  // debug override of the MN-major descriptor strides
+
+// ------------------------------------------------------------------------------------------------
+// TMA tensor maps (host).  cuTensorMapEncodeTiled is fetched through the runtime so libcuda is not a link-time
+// dependency (the library must load on a CPU-only box for the symbol test).
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  uint64_t d0, d1, stride;
+  uint32_t b0, b1;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && stride == o.stride && b0 == o.b0 && b1 == o.b1;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    h ^= k.d0 * 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    h ^= k.d1 * 0xC2B2AE3D27D4EB4Full + (h << 6) + (h >> 2);
+    h ^= k.stride * 0x165667B19E3779F9ull + (h << 6) + (h >> 2);
+    h ^= (uint64_t(k.b0) << 32 | k.b1) + (h << 6) + (h >> 2);
+    return h;
+  }
+};
+static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+static std::mutex g_maps_mu;
+
+// 2-D bf16 tensor, dim0 = contiguous (d0 elements), dim1 rows (d1) with `stride` elements between rows;
+// box = b0 x b1 elements, 128-byte swizzle (b0 * 2 bytes must be 128).
+static int make_map(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t stride, uint32_t b0,
+                    uint32_t b1) {
+  MapKey key{ptr, d0, d1, stride, b0, b1};
+  {
+    std::lock_guard<std::mutex> g(g_maps_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) {
+      *out = it->second;
+      return 0;
+    }
+  }
+  EncodeTiledFn enc = get_encode();
+  DSVG_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  DSVG_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA operand not 16-byte aligned");
+  DSVG_CHECK((stride * 2) % 16 == 0, "TMA operand row stride must be a multiple of 8 elements (got %llu)",
+             (unsigned long long)stride);
+  cuuint64_t dims[2] = {d0, d1};
+  cuuint64_t strides[1] = {stride * 2};
+  cuuint32_t box[2] = {b0, b1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DSVG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (dims %llu x %llu, stride %llu)",
+             int(r), (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)stride);
+  {
+    std::lock_guard<std::mutex> g(g_maps_mu);
+    if (g_maps.size() > 4096) g_maps.clear();
+    g_maps.emplace(key, *out);
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared epilogue
+// ------------------------------------------------------------------------------------------------
+struct Epi {
+  const float* bias;
+  int scale_cols;
+  float scale;
+  int relu;
+  Dropout drop;
+  const float* rowvec;
+  int rowvec_ld;
+  int rows_per_group;
+  const bf16* mask;
+  size_t mask_lo_off;
+  int mask_ld;
+  float mask_scale;
+  const float* residual;
+  int res_ld;
+  float* out_f32;
+  int out_f32_ld;
+  bf16* out_act;
+  size_t out_lo_off;
+  int out_act_ld;
+  int vec;  // 1: every pointer/stride satisfies the 4-wide vector path
+};
+
+constexpr int kThreads = 192;       // 6 warps
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;         // 64 bf16 = 128 bytes = one swizzle span
+constexpr int kStageRow = 36;       // fp32 staging row stride in words: 16-byte aligned rows, conflict-free v4 access
+constexpr int kStageWarpBytes = 32 * kStageRow * 4;
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+// scalar epilogue of one element (row, col): everything after the accumulator
+__device__ __forceinline__ void epi_scalar(float x, long long row, int col, int N, const Epi& ep) {
+  if (ep.bias != nullptr) x += __ldg(ep.bias + col);
+  if (col < ep.scale_cols) x *= ep.scale;
+  if (ep.relu) x = fmaxf(x, 0.f);
+  if (ep.drop.p > 0.f) x *= dropout_mult(ep.drop, (unsigned long long)row * (unsigned long long)N + col);
+  if (ep.rowvec != nullptr) x += __ldg(ep.rowvec + (long long)(int(row) / ep.rows_per_group) * ep.rowvec_ld + col);
+  if (ep.mask != nullptr) {
+    float m = act_load(ep.mask, ep.mask_lo_off, size_t(row) * ep.mask_ld + col);
+    x = (m != 0.f) ? x * ep.mask_scale : 0.f;
+  }
+  if (ep.residual != nullptr) x += ep.residual[row * (long long)ep.res_ld + col];
+  if (ep.out_f32 != nullptr) ep.out_f32[row * (long long)ep.out_f32_ld + col] = x;
+  if (ep.out_act != nullptr) act_store(ep.out_act, ep.out_lo_off, size_t(row) * ep.out_act_ld + col, x);
+}
+
+__device__ __forceinline__ float4 ld_bf16x4(const bf16* p) {
+  uint2 u = *reinterpret_cast<const uint2*>(p);
+  float2 a = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u.x));
+  float2 b = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void st_act4(bf16* p, size_t lo_off, size_t i, float4 x) {
+  __nv_bfloat162 h0 = __floats2bfloat162_rn(x.x, x.y), h1 = __floats2bfloat162_rn(x.z, x.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&h0);
+  u.y = *reinterpret_cast<uint32_t*>(&h1);
+  *reinterpret_cast<uint2*>(p + i) = u;
+  if (lo_off) {
+    float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+    __nv_bfloat162 l0 = __floats2bfloat162_rn(x.x - f0.x, x.y - f0.y), l1 = __floats2bfloat162_rn(x.z - f1.x, x.w - f1.y);
+    u.x = *reinterpret_cast<uint32_t*>(&l0);
+    u.y = *reinterpret_cast<uint32_t*>(&l1);
+    *reinterpret_cast<uint2*>(p + i + lo_off) = u;
+  }
+}
+
+// 4 consecutive columns of one row, all vector accesses aligned (host guarantees ep.vec preconditions)
+__device__ __forceinline__ void epi_vec4(float4 x, long long row, int col, int N, const Epi& ep, const float4& bias4) {
+  x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w;
+  if (ep.scale_cols > 0) {
+    if (col + 0 < ep.scale_cols) x.x *= ep.scale;
+    if (col + 1 < ep.scale_cols) x.y *= ep.scale;
+    if (col + 2 < ep.scale_cols) x.z *= ep.scale;
+    if (col + 3 < ep.scale_cols) x.w *= ep.scale;
+  }
+  if (ep.relu) {
+    x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
+  }
+  if (ep.drop.p > 0.f) {
+    float4 m = dropout_mult4(ep.drop, (unsigned long long)row * (unsigned long long)N + col);
+    x.x *= m.x; x.y *= m.y; x.z *= m.z; x.w *= m.w;
+  }
+  if (ep.rowvec != nullptr) {
+    float4 g = __ldg(reinterpret_cast<const float4*>(ep.rowvec + (long long)(int(row) / ep.rows_per_group) * ep.rowvec_ld + col));
+    x.x += g.x; x.y += g.y; x.z += g.z; x.w += g.w;
+  }
+  if (ep.mask != nullptr) {
+    size_t mi = size_t(row) * ep.mask_ld + col;
+    float4 m = ld_bf16x4(ep.mask + mi);
+    if (ep.mask_lo_off) {
+      float4 l = ld_bf16x4(ep.mask + mi + ep.mask_lo_off);
+      m.x += l.x; m.y += l.y; m.z += l.z; m.w += l.w;
+    }
+    x.x = m.x != 0.f ? x.x * ep.mask_scale : 0.f;
+    x.y = m.y != 0.f ? x.y * ep.mask_scale : 0.f;
+    x.z = m.z != 0.f ? x.z * ep.mask_scale : 0.f;
+    x.w = m.w != 0.f ? x.w * ep.mask_scale : 0.f;
+  }
+  if (ep.residual != nullptr) {
+    float4 r = *reinterpret_cast<const float4*>(ep.residual + row * (long long)ep.res_ld + col);
+    x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
+  }
+  if (ep.out_f32 != nullptr) *reinterpret_cast<float4*>(ep.out_f32 + row * (long long)ep.out_f32_ld + col) = x;
+  if (ep.out_act != nullptr) st_act4(ep.out_act, ep.out_lo_off, size_t(row) * ep.out_act_ld + col, x);
+}
+
+// Processes 32 accumulator columns held one-row-per-thread (straight out of tcgen05.ld), transposing them through
+// this warp's private shared-memory tile so that every global access is a coalesced row segment.
+//   v[j]       : accumulator of row (row0 + lane), column (col0 + j)
+//   stage_addr : shared-space byte address of this warp's [32][36] fp32 staging tile
+template <bool kOuter>
+__device__ __forceinline__ void epilogue_chunk(uint32_t (&v)[32], uint32_t stage_addr, int lane, long long row0, int col0,
+                                               int M, int N, const Epi& ep, float alpha, float* C, int ldc) {
+  {
+    const uint32_t my = stage_addr + lane * (kStageRow * 4);
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      st_shared_v4(my + q * 16, __uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                   __uint_as_float(v[4 * q + 3]));
+  }
+  __syncwarp();
+  if constexpr (kOuter) {
+    const int col = col0 + lane;
+#pragma unroll 4
+    for (int r = 0; r < 32; ++r) {
+      long long row = row0 + r;
+      float x = ld_shared_f32(stage_addr + (r * kStageRow + lane) * 4);
+      if (row < M && col < N) atomicAdd(C + row * (long long)ldc + col, x * alpha);
+    }
+  } else if (ep.vec) {
+    const int cg = lane & 7, rsub = lane >> 3;
+    const int col = col0 + 4 * cg;
+    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ep.bias != nullptr && col < N) bias4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
+#pragma unroll 2
+    for (int i = 0; i < 8; ++i) {
+      const int rl = 4 * i + rsub;
+      float4 x = ld_shared_v4(stage_addr + (rl * kStageRow + 4 * cg) * 4);
+      long long row = row0 + rl;
+      if (row < M && col < N) epi_vec4(x, row, col, N, ep, bias4);
+    }
+  } else {
+    const int col = col0 + lane;
+#pragma unroll 4
+    for (int r = 0; r < 32; ++r) {
+      long long row = row0 + r;
+      float x = ld_shared_f32(stage_addr + (r * kStageRow + lane) * 4);
+      if (row < M && col < N) epi_scalar(x, row, col, N, ep);
+    }
+  }
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
+// dsvg_linear kernel
+// ------------------------------------------------------------------------------------------------
+template <int BN, int NPLANES>
+struct LinearCfg {
+  static constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB
+  static constexpr int kBBytes = BN * kBlockK * 2;       // 16/32 KB
+  static constexpr int kStageBytes = NPLANES * (kABytes + kBBytes);
+  static constexpr int kStages = (NPLANES == 1) ? 4 : 2;
+  static constexpr int kTmemCols = 2 * BN;  // two accumulator stages (256 or 512: powers of two)
+  static constexpr int kStagingBytes = 4 * kStageWarpBytes;
+  static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kStagingBytes + 256;
+};
+
+template <int BN, int NPLANES>
+__global__ void __launch_bounds__(kThreads, 1)
+linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
+              const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo, int M, int N, int K,
+              Epi ep) {
+  using Cfg = LinearCfg<BN, NPLANES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* tiles = smem;
+  float* staging = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kStagingBytes);
+  uint64_t* full_bar = bars;                       // [kStages]
+  uint64_t* empty_bar = bars + Cfg::kStages;       // [kStages]
+  uint64_t* tfull_bar = bars + 2 * Cfg::kStages;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (NPLANES == 2) {
+      tma_prefetch_desc(&tmAlo);
+      tma_prefetch_desc(&tmBlo);
+    }
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int m_tiles = (M + kBlockM - 1) / kBlockM;
+  const int n_tiles = (N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_kb = (K + kBlockK - 1) / kBlockK;
+
+  if (warp == 0) {
+    // =================== TMA producer ===================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * kBlockM;
+        const int n0 = (tile % n_tiles) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = tiles + stage * Cfg::kStageBytes;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_2d(st, &tmA, &full_bar[stage], kb * kBlockK, m0);
+          tma_load_2d(st + Cfg::kABytes, &tmB, &full_bar[stage], kb * kBlockK, n0);
+          if (NPLANES == 2) {
+            tma_load_2d(st + Cfg::kABytes + Cfg::kBBytes, &tmAlo, &full_bar[stage], kb * kBlockK, m0);
+            tma_load_2d(st + 2 * Cfg::kABytes + Cfg::kBBytes, &tmBlo, &full_bar[stage], kb * kBlockK, n0);
+          }
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =================== MMA issuer ===================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(tiles + stage * Cfg::kStageBytes);
+          const uint32_t b_hi = a_hi + Cfg::kABytes;
+          const uint32_t a_lo = b_hi + Cfg::kBBytes;
+          const uint32_t b_lo = a_lo + Cfg::kABytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            uint64_t ad = umma_smem_desc(a_hi + k * 32, 16, 1024);
+            uint64_t bd = umma_smem_desc(b_hi + k * 32, 16, 1024);
+            umma_f16(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          if (NPLANES == 2) {
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              uint64_t ad = umma_smem_desc(a_hi + k * 32, 16, 1024);
+              uint64_t bd = umma_smem_desc(b_lo + k * 32, 16, 1024);
+              umma_f16(d_tmem, ad, bd, idesc, 1u);
+            }
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              uint64_t ad = umma_smem_desc(a_lo + k * 32, 16, 1024);
+              uint64_t bd = umma_smem_desc(b_hi + k * 32, 16, 1024);
+              umma_f16(d_tmem, ad, bd, idesc, 1u);
+            }
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete
+      }
+    }
+  } else {
+    // =================== epilogue warps (2..5) ===================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+    const uint32_t stage_buf = smem_u32(staging) + (warp - 2) * kStageWarpBytes;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m0 = (tile / n_tiles) * kBlockM;
+      const int n0 = (tile % n_tiles) * BN;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const long long row0 = (long long)m0 + quarter * 32;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        if (n0 + c >= N) break;
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * BN + c), v);
+        tmem_ld_wait();
+        epilogue_chunk<false>(v, stage_buf, lane, row0, n0 + c, M, N, ep, 1.f, nullptr, 0);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// dsvg_outer kernel (MN-major operands): one output tile [128 x BQ] per CTA, contraction over an M range
+// ------------------------------------------------------------------------------------------------
+template <int BQ, int NPLANES>
+struct OuterCfg {
+  static constexpr int kBoxBytes = 64 * 64 * 2;                 // [64 rows(m) x 64 cols] = 8 KB
+  static constexpr int kABytes = 2 * kBoxBytes;                 // 128 P columns
+  static constexpr int kBBytes = (BQ / 64) * kBoxBytes;         // BQ Q columns
+  static constexpr int kStageBytes = NPLANES * (kABytes + kBBytes);
+  static constexpr int kStages = (NPLANES == 1) ? 4 : 2;
+  static constexpr int kTmemCols = BQ;
+  static constexpr int kStagingBytes = 4 * kStageWarpBytes;
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kStagingBytes + 256;
+};
+
+template <int BQ, int NPLANES>
+__global__ void __launch_bounds__(kThreads, 1)
+outer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
+             const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo, int M, int P, int Q,
+             int mblk_per_split, float alpha, float* C, int ldc, uint32_t lbo, uint32_t sbo) {
+  using Cfg = OuterCfg<BQ, NPLANES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* tiles = smem;
+  float* staging = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kStagingBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::kStages;
+  uint64_t* tfull_bar = bars + 2 * Cfg::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int q_tiles = (Q + BQ - 1) / BQ;
+  const int p0 = (blockIdx.x / q_tiles) * 128;
+  const int q0 = (blockIdx.x % q_tiles) * BQ;
+  const int total_mblk = (M + 63) / 64;
+  const int mb_begin = blockIdx.y * mblk_per_split;
+  const int mb_end = min(total_mblk, mb_begin + mblk_per_split);
+  const int num_mb = mb_end - mb_begin;  // >= 1 by construction of the grid
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int mb = mb_begin; mb < mb_end; ++mb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* st = tiles + stage * Cfg::kStageBytes;
+        mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) tma_load_2d(st + i * Cfg::kBoxBytes, &tmA, &full_bar[stage], p0 + 64 * i, mb * 64);
+#pragma unroll
+        for (int j = 0; j < BQ / 64; ++j)
+          tma_load_2d(st + Cfg::kABytes + j * Cfg::kBoxBytes, &tmB, &full_bar[stage], q0 + 64 * j, mb * 64);
+        if (NPLANES == 2) {
+          uint8_t* lo = st + Cfg::kABytes + Cfg::kBBytes;
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+            tma_load_2d(lo + i * Cfg::kBoxBytes, &tmAlo, &full_bar[stage], p0 + 64 * i, mb * 64);
+#pragma unroll
+          for (int j = 0; j < BQ / 64; ++j)
+            tma_load_2d(lo + Cfg::kABytes + j * Cfg::kBoxBytes, &tmBlo, &full_bar[stage], q0 + 64 * j, mb * 64);
+        }
+        if (++stage == Cfg::kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BQ, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < num_mb; ++i) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(tiles + stage * Cfg::kStageBytes);
+        const uint32_t b_hi = a_hi + Cfg::kABytes;
+        const uint32_t a_lo = b_hi + Cfg::kBBytes;
+        const uint32_t b_lo = a_lo + Cfg::kABytes;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // 16 rows (= 2 KB) of the 64-row block per UMMA
+          uint64_t ad = umma_smem_desc(a_hi + k * 2048, lbo, sbo);
+          uint64_t bd = umma_smem_desc(b_hi + k * 2048, lbo, sbo);
+          umma_f16(tmem_base, ad, bd, idesc, (i | k) != 0 ? 1u : 0u);
+        }
+        if (NPLANES == 2) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            uint64_t ad = umma_smem_desc(a_hi + k * 2048, lbo, sbo);
+            uint64_t bd = umma_smem_desc(b_lo + k * 2048, lbo, sbo);
+            umma_f16(tmem_base, ad, bd, idesc, 1u);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            uint64_t ad = umma_smem_desc(a_lo + k * 2048, lbo, sbo);
+            uint64_t bd = umma_smem_desc(b_hi + k * 2048, lbo, sbo);
+            umma_f16(tmem_base, ad, bd, idesc, 1u);
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == Cfg::kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(tfull_bar);
+    }
+  } else {
+    const int quarter = warp & 3;
+    const uint32_t stage_buf = smem_u32(staging) + (warp - 2) * kStageWarpBytes;
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+    Epi dummy{};
+#pragma unroll 1
+    for (int c = 0; c < BQ; c += 32) {
+      if (q0 + c >= Q) break;
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(c), v);
+      tmem_ld_wait();
+      epilogue_chunk<true>(v, stage_buf, lane, (long long)p0 + quarter * 32, q0 + c, P, Q, dummy, alpha, C, ldc);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN, int NPLANES>
+static int launch_linear(const CUtensorMap& a, const CUtensorMap& alo, const CUtensorMap& b, const CUtensorMap& blo,
+                         int M, int N, int K, const Epi& ep, cudaStream_t st) {
+  using Cfg = LinearCfg<BN, NPLANES>;
+  static bool configured = false;
+  if (!configured) {
+    DSVG_CUDA(cudaFuncSetAttribute(linear_kernel<BN, NPLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int tiles = ceil_div(M, kBlockM) * ceil_div(N, BN);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  linear_kernel<BN, NPLANES><<<grid, kThreads, Cfg::kSmemBytes, st>>>(a, alo, b, blo, M, N, K, ep);
+  ++g_launches;
+  DSVG_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int BQ, int NPLANES>
+static int launch_outer(const CUtensorMap& a, const CUtensorMap& alo, const CUtensorMap& b, const CUtensorMap& blo,
+                        int M, int P, int Q, float alpha, float* C, int ldc, cudaStream_t st) {
+  using Cfg = OuterCfg<BQ, NPLANES>;
+  static bool configured = false;
+  if (!configured) {
+    DSVG_CUDA(cudaFuncSetAttribute(outer_kernel<BQ, NPLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int out_tiles = ceil_div(P, 128) * ceil_div(Q, BQ);
+  const int total_mblk = ceil_div(M, 64);
+  int splits = (2 * sm_count() + out_tiles - 1) / out_tiles;  // ~2 CTAs per SM in flight over the launch
+  if (splits > total_mblk / 4) splits = total_mblk / 4;       // keep >= 4 blocks of 64 rows per split
+  if (splits < 1) splits = 1;
+  const int per = ceil_div(total_mblk, splits);
+  splits = ceil_div(total_mblk, per);
+  dim3 grid(out_tiles, splits);
+  outer_kernel<BQ, NPLANES><<<grid, kThreads, Cfg::kSmemBytes, st>>>(a, alo, b, blo, M, P, Q, per, alpha, C, ldc,
+                                                                      g_outer_lbo ? g_outer_lbo : Cfg::kBoxBytes,
+                                                                      g_outer_sbo ? g_outer_sbo : 1024u);
+  ++g_launches;
+  DSVG_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace dsvg
+
+using namespace dsvg;
+
+extern "C" const char* dsvg_last_error(void) { return dsvg::last_error(); }
+extern "C" int dsvg_abi_version(void) { return 1; }
+extern "C" void dsvg_debug_outer_desc(unsigned lbo, unsigned sbo) {
+  dsvg::g_outer_lbo = lbo;
+  dsvg::g_outer_sbo = sbo;
+}
+extern "C" unsigned long long dsvg_launch_count(void) { return dsvg::g_launches; }
+
+extern "C" int dsvg_linear(const dsvg_bf16* X, size_t x_lo_off, int lda, const dsvg_bf16* W, size_t w_lo_off, int ldb,
+                           int M, int N, int K, const dsvg_epilogue* e, void* stream) {
+  DSVG_CHECK(X && W && e, "dsvg_linear: null pointer");
+  DSVG_CHECK(M > 0 && N > 0 && K > 0, "dsvg_linear: bad shape %d x %d x %d", M, N, K);
+  DSVG_CHECK(K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0, "dsvg_linear: K/lda/ldb must be multiples of 8");
+  DSVG_CHECK((x_lo_off == 0) == (w_lo_off == 0), "dsvg_linear: both operands must have the same number of planes");
+  Epi ep{};
+  ep.bias = e->bias;
+  ep.scale_cols = e->scale_cols;
+  ep.scale = e->scale;
+  ep.relu = e->relu;
+  ep.drop = make_dropout(e->drop_p, e->drop_site, e->seed);
+  ep.rowvec = e->rowvec;
+  ep.rowvec_ld = e->rowvec_ld;
+  ep.rows_per_group = e->rows_per_group > 0 ? e->rows_per_group : 1;
+  ep.mask = reinterpret_cast<const bf16*>(e->mask);
+  ep.mask_lo_off = e->mask_lo_off;
+  ep.mask_ld = e->mask_ld;
+  ep.mask_scale = e->mask_scale;
+  ep.residual = e->residual;
+  ep.res_ld = e->res_ld;
+  ep.out_f32 = e->out_f32;
+  ep.out_f32_ld = e->out_f32_ld;
+  ep.out_act = reinterpret_cast<bf16*>(e->out_act);
+  ep.out_lo_off = e->out_lo_off;
+  ep.out_act_ld = e->out_act_ld;
+  DSVG_CHECK(ep.out_f32 || ep.out_act, "dsvg_linear: no output requested");
+  {
+    auto al = [](const void* p, size_t a) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % a) == 0; };
+    bool v = (N % 4 == 0) && al(ep.bias, 16) && al(ep.rowvec, 16) && al(ep.residual, 16) && al(ep.out_f32, 16) &&
+             al(ep.mask, 8) && al(ep.out_act, 8);
+    v = v && (!ep.rowvec || ep.rowvec_ld % 4 == 0) && (!ep.residual || ep.res_ld % 4 == 0) &&
+        (!ep.out_f32 || ep.out_f32_ld % 4 == 0) && (!ep.mask || (ep.mask_ld % 4 == 0 && ep.mask_lo_off % 4 == 0)) &&
+        (!ep.out_act || (ep.out_act_ld % 4 == 0 && ep.out_lo_off % 4 == 0));
+    ep.vec = v ? 1 : 0;
+  }
+  const bool wide = (N > 128);
+  const uint32_t bn = wide ? 256 : 128;
+  CUtensorMap a, alo, b, blo;
+  const bf16* Xb = reinterpret_cast<const bf16*>(X);
+  const bf16* Wb = reinterpret_cast<const bf16*>(W);
+  if (make_map(&a, Xb, K, M, lda, 64, 128)) return 1;
+  if (make_map(&b, Wb, K, N, ldb, 64, bn)) return 1;
+  alo = a;
+  blo = b;
+  const bool split = x_lo_off != 0;
+  if (split) {
+    if (make_map(&alo, Xb + x_lo_off, K, M, lda, 64, 128)) return 1;
+    if (make_map(&blo, Wb + w_lo_off, K, N, ldb, 64, bn)) return 1;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (wide) return split ? launch_linear<256, 2>(a, alo, b, blo, M, N, K, ep, st)
+                         : launch_linear<256, 1>(a, alo, b, blo, M, N, K, ep, st);
+  return split ? launch_linear<128, 2>(a, alo, b, blo, M, N, K, ep, st)
+               : launch_linear<128, 1>(a, alo, b, blo, M, N, K, ep, st);
+}
+
+extern "C" int dsvg_outer(const dsvg_bf16* A, size_t a_lo_off, int lda, const dsvg_bf16* B, size_t b_lo_off, int ldb,
+                          int M, int P, int Q, float alpha, float* C, int ldc, void* stream) {
+  DSVG_CHECK(A && B && C, "dsvg_outer: null pointer");
+  DSVG_CHECK(M > 0 && P > 0 && Q > 0, "dsvg_outer: bad shape");
+  DSVG_CHECK(lda % 8 == 0 && ldb % 8 == 0, "dsvg_outer: lda/ldb must be multiples of 8");
+  DSVG_CHECK((a_lo_off == 0) == (b_lo_off == 0), "dsvg_outer: both operands must have the same number of planes");
+  const bool wide = (Q > 128);
+  CUtensorMap a, alo, b, blo;
+  const bf16* Ab = reinterpret_cast<const bf16*>(A);
+  const bf16* Bb = reinterpret_cast<const bf16*>(B);
+  // dim0 = feature columns (contiguous), dim1 = M rows; the tensor extents clip (zero-fill) ragged edges
+  if (make_map(&a, Ab, P, M, lda, 64, 64)) return 1;
+  if (make_map(&b, Bb, Q, M, ldb, 64, 64)) return 1;
+  alo = a;
+  blo = b;
+  const bool split = a_lo_off != 0;
+  if (split) {
+    if (make_map(&alo, Ab + a_lo_off, P, M, lda, 64, 64)) return 1;
+    if (make_map(&blo, Bb + b_lo_off, Q, M, ldb, 64, 64)) return 1;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (wide) return split ? launch_outer<256, 2>(a, alo, b, blo, M, P, Q, alpha, C, ldc, st)
+                         : launch_outer<256, 1>(a, alo, b, blo, M, P, Q, alpha, C, ldc, st);
+  return split ? launch_outer<128, 2>(a, alo, b, blo, M, P, Q, alpha, C, ldc, st)
+               : launch_outer<128, 1>(a, alo, b, blo, M, P, Q, alpha, C, ldc, st);
+}

@@ -1,0 +1,147 @@
+"""Generates tests/golden/*.npz by EXECUTING THE REFERENCE (alexandre01/deepsvg, mounted at /root/reference).
+
+Run once in the authoring container:  python tests/golden/make_golden.py
+The reference cannot travel to the GPU box, so its outputs are committed as fixtures; tests/test_oracle_golden.py
+pins oracle/svg_oracle.py against them.  Nothing from the reference is copied: it is imported, run, and only
+numbers are stored.
+
+Protocol: eval mode (dropout off), VAE noise injected, and the loss's aliased in-place
+`_get_padding_mask(extended=True)` replaced by its clean clone()-based equivalent ("de-aliased oracle").
+"""
+import os
+import sys
+from unittest.mock import MagicMock
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+for m in ["tensorboardX", "cairosvg", "IPython", "IPython.display", "moviepy", "moviepy.editor", "shapely",
+          "shapely.ops", "shapely.geometry", "matplotlib", "matplotlib.pyplot", "svgwrite"]:
+    sys.modules.setdefault(m, MagicMock())
+
+from deepsvg.model import loss as ref_loss_mod          # noqa: E402
+from deepsvg.model import utils as ref_utils            # noqa: E402
+from deepsvg.model.config import Hierarchical, OneStageOneShot  # noqa: E402
+from deepsvg.model.loss import SVGLoss                  # noqa: E402
+from deepsvg.model.model import SVGTransformer          # noqa: E402
+
+from oracle import svg_oracle as O                      # noqa: E402
+
+
+def dealiased_padding_mask(commands, seq_dim=0, extended=False):
+    """Same arithmetic as the reference's _get_padding_mask, but the shifted add reads a copy (no aliasing)."""
+    with torch.no_grad():
+        pm = ((commands == 4).cumsum(dim=seq_dim) == 0).float()
+        if extended:
+            S = commands.size(seq_dim)
+            src = torch.narrow(pm, seq_dim, 0, S - 3).clone()
+            torch.narrow(pm, seq_dim, 3, S - 3).add_(src).clamp_(max=1)
+        if seq_dim == 0:
+            return pm.unsqueeze(-1)
+        return pm
+
+
+ref_loss_mod._get_padding_mask = dealiased_padding_mask
+
+CASES = {
+    # name: (kind, overrides, batch, store_full)
+    "tiny_hier": ("hierarchical", dict(d_model=32, n_heads=4, dim_feedforward=64, dim_z=24, n_layers=2,
+                                       n_layers_decode=2, max_num_groups=3, max_seq_len=6, args_dim=15,
+                                       use_vae=False), 3, True),
+    "tiny_hier_vae_label": ("hierarchical", dict(d_model=32, n_heads=2, dim_feedforward=48, dim_z=16, n_layers=1,
+                                                 n_layers_decode=2, max_num_groups=4, max_seq_len=5, args_dim=15,
+                                                 use_vae=True, label_condition=True, n_labels=7, dim_label=8),
+                            4, True),
+    "tiny_one_stage": ("one_stage", dict(d_model=32, n_heads=4, dim_feedforward=64, dim_z=32, n_layers=2,
+                                         n_layers_decode=1, max_num_groups=4, max_total_len=12, args_dim=15,
+                                         use_vae=True, label_condition=True, n_labels=5, dim_label=8), 3, True),
+    "hier_cfg1": ("hierarchical", dict(use_vae=False), 2, False),   # BASELINE.json configs[0]
+}
+WEIGHTS = dict(O.DEFAULT_WEIGHTS)
+
+
+def ref_cfg(kind, over):
+    c = Hierarchical() if kind == "hierarchical" else OneStageOneShot()
+    for k, v in over.items():
+        setattr(c, k, v)
+    if "max_total_len" not in over:
+        c.max_total_len = c.max_num_groups * c.max_seq_len
+    c.num_groups_proposal = c.max_num_groups
+    return c
+
+
+def sample(t, n=4096):
+    f = t.reshape(-1)
+    if f.numel() <= n:
+        return f.clone()
+    idx = torch.linspace(0, f.numel() - 1, n).long()
+    return f[idx]
+
+
+def run_case(name):
+    kind, over, batch, full = CASES[name]
+    cfg_o = O.make_cfg(kind, **over)
+    cfg_r = ref_cfg(kind, over)
+    params = O.make_params(cfg_o, seed=7)
+    model = SVGTransformer(cfg_r)
+    sd = model.state_dict()
+    # the oracle's parameter inventory must be exactly the reference's parameters
+    ref_param_names = {k for k, _ in model.named_parameters()}
+    assert ref_param_names == set(params), (ref_param_names ^ set(params))
+    for k, v in params.items():
+        assert tuple(sd[k].shape) == tuple(v.shape), (k, sd[k].shape, v.shape)
+    model.load_state_dict(params, strict=False)
+    model.eval()
+    loss_fn = SVGLoss(cfg_r)
+    cmd, arg = O.synth_batch(cfg_o, batch, seed=99)
+    label = None
+    kw = {}
+    if cfg_o.label_condition:
+        label = torch.randint(0, cfg_o.n_labels, (batch,), generator=torch.Generator().manual_seed(5))
+        kw["label"] = label
+    eps = None
+    if cfg_o.use_vae:
+        eps = torch.randn(batch, cfg_o.dim_z, generator=torch.Generator().manual_seed(6))
+        real = torch.randn_like
+        torch.randn_like = lambda s, *a, **k: eps.reshape(s.shape).to(s.dtype)
+    try:
+        out = model(cmd, arg, cmd, arg, params={}, **kw)
+    finally:
+        if cfg_o.use_vae:
+            torch.randn_like = real
+    losses = loss_fn(out, None, weights=WEIGHTS)
+    model.zero_grad()
+    losses["loss"].backward()
+    grads = {k: (p.grad if p.grad is not None else torch.zeros_like(p)) for k, p in model.named_parameters()}
+
+    fx = {"commands": cmd.numpy(), "args": arg.numpy(), "seed_params": np.int64(7)}
+    if label is not None:
+        fx["label"] = label.numpy()
+    if eps is not None:
+        fx["eps"] = eps.numpy()
+    for k in ("loss", "loss_cmd", "loss_args", "loss_visibility", "loss_kl"):
+        if k in losses:
+            fx["L_" + k] = np.float64(losses[k].item())
+    keys = ["command_logits", "args_logits"] + (["visibility_logits"] if "visibility_logits" in out else []) + \
+           (["mu", "logsigma"] if "mu" in out else [])
+    for k in keys:
+        t = out[k].detach().contiguous()
+        fx["O_shape_" + k] = np.array(t.shape)
+        fx["O_" + k] = (t if full else sample(t)).numpy()
+    fx["param_names"] = np.array(sorted(grads))
+    for k, g in grads.items():
+        fx["Gnorm_" + k] = np.float64(g.double().norm().item())
+        fx["G_" + k] = (g if full else sample(g, 512)).detach().numpy()
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **fx)
+    print(name, {k: float(v) for k, v in fx.items() if k.startswith("L_")}, os.path.getsize(path) // 1024, "KB")
+
+
+if __name__ == "__main__":
+    torch.manual_seed(0)
+    for n in (sys.argv[1:] or CASES):
+        run_case(n)

@@ -1,0 +1,29 @@
+"""The fixture cases of tests/golden/make_golden.py, restated so the tests do not import the generator
+(which needs /root/reference)."""
+import os
+
+import numpy as np
+
+from oracle import svg_oracle as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+CASES = {
+    "tiny_hier": ("hierarchical", dict(d_model=32, n_heads=4, dim_feedforward=64, dim_z=24, n_layers=2,
+                                       n_layers_decode=2, max_num_groups=3, max_seq_len=6, args_dim=15,
+                                       use_vae=False), True),
+    "tiny_hier_vae_label": ("hierarchical", dict(d_model=32, n_heads=2, dim_feedforward=48, dim_z=16, n_layers=1,
+                                                 n_layers_decode=2, max_num_groups=4, max_seq_len=5, args_dim=15,
+                                                 use_vae=True, label_condition=True, n_labels=7, dim_label=8), True),
+    "tiny_one_stage": ("one_stage", dict(d_model=32, n_heads=4, dim_feedforward=64, dim_z=32, n_layers=2,
+                                         n_layers_decode=1, max_num_groups=4, max_total_len=12, args_dim=15,
+                                         use_vae=True, label_condition=True, n_labels=5, dim_label=8), True),
+    "hier_cfg1": ("hierarchical", dict(use_vae=False), False),
+}
+
+
+def load_case(name):
+    kind, over, full = CASES[name]
+    cfg = O.make_cfg(kind, **over)
+    fx = dict(np.load(os.path.join(HERE, "golden", name + ".npz"), allow_pickle=False))
+    return cfg, fx, full

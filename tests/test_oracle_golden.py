@@ -1,0 +1,76 @@
+"""Pins oracle/svg_oracle.py against fixtures produced by executing the reference (tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import svg_oracle as O
+from tests.golden_cases import CASES, load_case
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _strided(t, n):
+    f = t.reshape(-1)
+    if f.numel() <= n:
+        return f
+    return f[torch.linspace(0, f.numel() - 1, n).long()]
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_oracle_matches_reference(name):
+    cfg, fx, full = load_case(name)
+    params = O.make_params(cfg, seed=int(fx["seed_params"]))
+    cmd, arg = torch.from_numpy(fx["commands"]), torch.from_numpy(fx["args"])
+    label = torch.from_numpy(fx["label"]) if "label" in fx else None
+    eps = torch.from_numpy(fx["eps"]) if "eps" in fx else None
+    out, losses, grads = O.train_step(params, cfg, cmd, arg, label=label, eps=eps)
+    # outputs
+    for k in ("command_logits", "args_logits", "visibility_logits", "mu", "logsigma"):
+        if "O_" + k not in fx:
+            assert k not in out
+            continue
+        assert tuple(out[k].shape) == tuple(fx["O_shape_" + k]), k
+        got = out[k] if full else _strided(out[k], 4096)
+        np.testing.assert_allclose(got.numpy().reshape(-1), fx["O_" + k].reshape(-1), rtol=2e-4, atol=2e-5, err_msg=k)
+    # every loss term
+    for k in ("loss", "loss_cmd", "loss_args", "loss_visibility", "loss_kl"):
+        if "L_" + k in fx:
+            assert abs(losses[k].item() - float(fx["L_" + k])) <= 1e-5 * max(1.0, abs(float(fx["L_" + k]))), k
+        else:
+            assert k not in losses
+    # every parameter gradient
+    assert sorted(grads) == list(fx["param_names"])
+    for k, g in grads.items():
+        ref_norm = float(fx["Gnorm_" + k])
+        got = g if full else _strided(g, 512)
+        # fp32 re-association noise only: tolerance relative to the largest entry of the tensor
+        tol = 1e-3 * float(np.abs(fx["G_" + k]).max()) + 1e-7
+        np.testing.assert_allclose(got.numpy().reshape(-1), fx["G_" + k].reshape(-1), rtol=2e-3, atol=tol, err_msg=k)
+        assert abs(g.double().norm().item() - ref_norm) <= 1e-3 * ref_norm + 1e-7, k
+
+
+def test_extended_padding_semantics():
+    # clean OR-shift-by-3: prefix of ones grows by 3, independent of prefix length
+    for ln in (1, 2, 5, 14, 20, 29):
+        cmd = torch.full((1, 1, 32), float(O.CMD_EOS))
+        cmd[0, 0, 0] = O.CMD_SOS
+        cmd[0, 0, 1:1 + ln] = O.CMD_L
+        ext = O.extended_padding(cmd.long())[0, 0]
+        k = 1 + ln
+        expect = torch.zeros(32)
+        expect[:min(32, k)] = 1
+        expect[3:min(32, k + 3)] = 1
+        assert torch.equal(ext, expect), ln
+
+
+def test_matmul_modes_are_close():
+    cfg, fx, _ = load_case("tiny_hier")
+    params = O.make_params(cfg, seed=7)
+    cmd, arg = torch.from_numpy(fx["commands"]), torch.from_numpy(fx["args"])
+    ref = O.forward(params, cfg, cmd, arg)["args_logits"]
+    x3 = O.forward(params, cfg, cmd, arg, matmul="bf16x3")["args_logits"]
+    b1 = O.forward(params, cfg, cmd, arg, matmul="bf16")["args_logits"]
+    e3, e1 = (x3 - ref).abs().max().item(), (b1 - ref).abs().max().item()
+    assert e3 < 2e-4 and e3 < e1 / 20, (e3, e1)
