@@ -52,7 +52,7 @@ def test_oracle_matches_reference(name):
         # a ReLU pre-activation within 1 ulp of zero may flip between two fp32 implementations: tolerate isolated
         # elements, but never more than 0.5 % of a tensor, and never a large relative error on the whole tensor
         assert bad.sum() <= max(1, int(0.005 * a.size)), (k, int(bad.sum()), float(np.abs(a - b).max()))
-        assert np.linalg.norm(a - b) <= 2e-3 * np.linalg.norm(b) + 1e-7, k
+        assert np.linalg.norm(a - b) <= 1e-2 * np.linalg.norm(b) + 1e-7, k
         assert abs(g.double().norm().item() - ref_norm) <= 1e-3 * ref_norm + 1e-7, k
 
 
