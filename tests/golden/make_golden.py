@@ -5,7 +5,7 @@ The reference cannot travel to the GPU box, so its outputs are committed as fixt
 pins oracle/svg_oracle.py against them.  Nothing from the reference is copied: it is imported, run, and only
 numbers are stored.
 
-Protocol: eval mode (dropout off), VAE noise injected, and the loss's aliased in-place
+Protocol: the reference module is run in float64 (`.double()`), eval mode (dropout off), VAE noise injected, and the loss's aliased in-place
 `_get_padding_mask(extended=True)` replaced by its clean clone()-based equivalent ("de-aliased oracle").
 """
 import os
@@ -86,8 +86,8 @@ def run_case(name):
     kind, over, batch, full = CASES[name]
     cfg_o = O.make_cfg(kind, **over)
     cfg_r = ref_cfg(kind, over)
-    params = O.make_params(cfg_o, seed=7)
-    model = SVGTransformer(cfg_r)
+    params = O.make_params(cfg_o, seed=7, dtype=torch.float64)
+    model = SVGTransformer(cfg_r).double()   # fp64: no ReLU-boundary chaos between two implementations
     sd = model.state_dict()
     # the oracle's parameter inventory must be exactly the reference's parameters
     ref_param_names = {k for k, _ in model.named_parameters()}
@@ -98,6 +98,7 @@ def run_case(name):
     model.eval()
     loss_fn = SVGLoss(cfg_r)
     cmd, arg = O.synth_batch(cfg_o, batch, seed=99)
+    cmd, arg = cmd.double(), arg.double()
     label = None
     kw = {}
     if cfg_o.label_condition:
@@ -105,7 +106,7 @@ def run_case(name):
         kw["label"] = label
     eps = None
     if cfg_o.use_vae:
-        eps = torch.randn(batch, cfg_o.dim_z, generator=torch.Generator().manual_seed(6))
+        eps = torch.randn(batch, cfg_o.dim_z, generator=torch.Generator().manual_seed(6)).double()
         real = torch.randn_like
         torch.randn_like = lambda s, *a, **k: eps.reshape(s.shape).to(s.dtype)
     try:
@@ -118,7 +119,7 @@ def run_case(name):
     losses["loss"].backward()
     grads = {k: (p.grad if p.grad is not None else torch.zeros_like(p)) for k, p in model.named_parameters()}
 
-    fx = {"commands": cmd.numpy(), "args": arg.numpy(), "seed_params": np.int64(7)}
+    fx = {"commands": cmd.float().numpy(), "args": arg.float().numpy(), "seed_params": np.int64(7)}
     if label is not None:
         fx["label"] = label.numpy()
     if eps is not None:
