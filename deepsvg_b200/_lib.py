@@ -15,6 +15,7 @@ _lib = None
 class Epilogue(C.Structure):
     """Mirror of `dsvg_epilogue` (include/dsvg_b200.h)."""
     _fields_ = [
+        ("acc_scale_dev", C.c_void_p),
         ("bias", C.c_void_p),
         ("scale_cols", C.c_int),
         ("scale", C.c_float),

@@ -117,6 +117,7 @@ static int make_map(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1,
 // shared epilogue
 // ------------------------------------------------------------------------------------------------
 struct Epi {
+  const float* acc_scale_dev;  // optional device scalar multiplying the accumulator first
   const float* bias;
   int scale_cols;
   float scale;
@@ -161,7 +162,8 @@ __device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
 }
 
 // scalar epilogue of one element (row, col): everything after the accumulator
-__device__ __forceinline__ void epi_scalar(float x, long long row, int col, int N, const Epi& ep) {
+__device__ __forceinline__ void epi_scalar(float x, long long row, int col, int N, const Epi& ep, float acc_scale) {
+  x *= acc_scale;
   if (ep.bias != nullptr) x += __ldg(ep.bias + col);
   if (col < ep.scale_cols) x *= ep.scale;
   if (ep.relu) x = fmaxf(x, 0.f);
@@ -198,7 +200,9 @@ __device__ __forceinline__ void st_act4(bf16* p, size_t lo_off, size_t i, float4
 }
 
 // 4 consecutive columns of one row, all vector accesses aligned (host guarantees ep.vec preconditions)
-__device__ __forceinline__ void epi_vec4(float4 x, long long row, int col, int N, const Epi& ep, const float4& bias4) {
+__device__ __forceinline__ void epi_vec4(float4 x, long long row, int col, int N, const Epi& ep, const float4& bias4,
+                                         float acc_scale) {
+  x.x *= acc_scale; x.y *= acc_scale; x.z *= acc_scale; x.w *= acc_scale;
   x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w;
   if (ep.scale_cols > 0) {
     if (col + 0 < ep.scale_cols) x.x *= ep.scale;
@@ -244,6 +248,7 @@ __device__ __forceinline__ void epi_vec4(float4 x, long long row, int col, int N
 template <bool kOuter>
 __device__ __forceinline__ void epilogue_chunk(uint32_t (&v)[32], uint32_t stage_addr, int lane, long long row0, int col0,
                                                int M, int N, const Epi& ep, float alpha, float* C, int ldc) {
+  const float acc_scale = (!kOuter && ep.acc_scale_dev != nullptr) ? __ldg(ep.acc_scale_dev) : 1.f;
   {
     const uint32_t my = stage_addr + lane * (kStageRow * 4);
 #pragma unroll
@@ -270,7 +275,7 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&v)[32], uint32_t stage
       const int rl = 4 * i + rsub;
       float4 x = ld_shared_v4(stage_addr + (rl * kStageRow + 4 * cg) * 4);
       long long row = row0 + rl;
-      if (row < M && col < N) epi_vec4(x, row, col, N, ep, bias4);
+      if (row < M && col < N) epi_vec4(x, row, col, N, ep, bias4, acc_scale);
     }
   } else {
     const int col = col0 + lane;
@@ -278,7 +283,7 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&v)[32], uint32_t stage
     for (int r = 0; r < 32; ++r) {
       long long row = row0 + r;
       float x = ld_shared_f32(stage_addr + (r * kStageRow + lane) * 4);
-      if (row < M && col < N) epi_scalar(x, row, col, N, ep);
+      if (row < M && col < N) epi_scalar(x, row, col, N, ep, acc_scale);
     }
   }
   __syncwarp();
@@ -478,7 +483,7 @@ template <int BQ, int NPLANES>
 __global__ void __launch_bounds__(kThreads, 1)
 outer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
              const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo, int M, int P, int Q,
-             int mblk_per_split, float alpha, float* C, int ldc, uint32_t lbo, uint32_t sbo) {
+             int mblk_per_split, float alpha, const float* alpha_dev, float* C, int ldc, uint32_t lbo, uint32_t sbo) {
   using Cfg = OuterCfg<BQ, NPLANES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -594,6 +599,7 @@ outer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     mbar_wait(tfull_bar, 0);
     tc_fence_after();
     Epi dummy{};
+    if (alpha_dev != nullptr) alpha *= __ldg(alpha_dev);
 #pragma unroll 1
     for (int c = 0; c < BQ; c += 32) {
       if (q0 + c >= Q) break;
@@ -644,7 +650,7 @@ static int launch_linear(const CUtensorMap& a, const CUtensorMap& alo, const CUt
 
 template <int BQ, int NPLANES>
 static int launch_outer(const CUtensorMap& a, const CUtensorMap& alo, const CUtensorMap& b, const CUtensorMap& blo,
-                        int M, int P, int Q, float alpha, float* C, int ldc, cudaStream_t st) {
+                        int M, int P, int Q, float alpha, const float* alpha_dev, float* C, int ldc, cudaStream_t st) {
   using Cfg = OuterCfg<BQ, NPLANES>;
   static bool configured = false;
   if (!configured) {
@@ -660,7 +666,7 @@ static int launch_outer(const CUtensorMap& a, const CUtensorMap& alo, const CUte
   const int per = ceil_div(total_mblk, splits);
   splits = ceil_div(total_mblk, per);
   dim3 grid(out_tiles, splits);
-  outer_kernel<BQ, NPLANES><<<grid, kThreads, Cfg::kSmemBytes, st>>>(a, alo, b, blo, M, P, Q, per, alpha, C, ldc,
+  outer_kernel<BQ, NPLANES><<<grid, kThreads, Cfg::kSmemBytes, st>>>(a, alo, b, blo, M, P, Q, per, alpha, alpha_dev, C, ldc,
                                                                       g_outer_lbo ? g_outer_lbo : Cfg::kBoxBytes,
                                                                       g_outer_sbo ? g_outer_sbo : 1024u);
   ++g_launches;
@@ -687,6 +693,7 @@ extern "C" int dsvg_linear(const dsvg_bf16* X, size_t x_lo_off, int lda, const d
   DSVG_CHECK(K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0, "dsvg_linear: K/lda/ldb must be multiples of 8");
   DSVG_CHECK((x_lo_off == 0) == (w_lo_off == 0), "dsvg_linear: both operands must have the same number of planes");
   Epi ep{};
+  ep.acc_scale_dev = e->acc_scale_dev;
   ep.bias = e->bias;
   ep.scale_cols = e->scale_cols;
   ep.scale = e->scale;
@@ -738,7 +745,7 @@ extern "C" int dsvg_linear(const dsvg_bf16* X, size_t x_lo_off, int lda, const d
 }
 
 extern "C" int dsvg_outer(const dsvg_bf16* A, size_t a_lo_off, int lda, const dsvg_bf16* B, size_t b_lo_off, int ldb,
-                          int M, int P, int Q, float alpha, float* C, int ldc, void* stream) {
+                          int M, int P, int Q, float alpha, const float* alpha_dev, float* C, int ldc, void* stream) {
   DSVG_CHECK(A && B && C, "dsvg_outer: null pointer");
   DSVG_CHECK(M > 0 && P > 0 && Q > 0, "dsvg_outer: bad shape");
   DSVG_CHECK(lda % 8 == 0 && ldb % 8 == 0, "dsvg_outer: lda/ldb must be multiples of 8");
@@ -758,8 +765,8 @@ extern "C" int dsvg_outer(const dsvg_bf16* A, size_t a_lo_off, int lda, const ds
     if (make_map(&blo, Bb + b_lo_off, Q, M, ldb, 64, 64)) return 1;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (wide) return split ? launch_outer<256, 2>(a, alo, b, blo, M, P, Q, alpha, C, ldc, st)
-                         : launch_outer<256, 1>(a, alo, b, blo, M, P, Q, alpha, C, ldc, st);
-  return split ? launch_outer<128, 2>(a, alo, b, blo, M, P, Q, alpha, C, ldc, st)
-               : launch_outer<128, 1>(a, alo, b, blo, M, P, Q, alpha, C, ldc, st);
+  if (wide) return split ? launch_outer<256, 2>(a, alo, b, blo, M, P, Q, alpha, alpha_dev, C, ldc, st)
+                         : launch_outer<256, 1>(a, alo, b, blo, M, P, Q, alpha, alpha_dev, C, ldc, st);
+  return split ? launch_outer<128, 2>(a, alo, b, blo, M, P, Q, alpha, alpha_dev, C, ldc, st)
+               : launch_outer<128, 1>(a, alo, b, blo, M, P, Q, alpha, alpha_dev, C, ldc, st);
 }

@@ -33,12 +33,13 @@ unsigned long long dsvg_launch_count(void);
 
 /* ---- dense contractions on the tcgen05 tensor cores ------------------------------------------------- */
 /* Fused epilogue of dsvg_linear, applied to the fp32 accumulator in this order:
- *   v = acc; v += bias[col]; if (col < scale_cols) v *= scale; if (relu) v = max(v,0);
+ *   v = acc * (*acc_scale_dev); v += bias[col]; if (col < scale_cols) v *= scale; if (relu) v = max(v,0);
  *   v *= dropout(p, seed, site, idx = row*N+col); v += rowvec[(row / rows_per_group)*rowvec_ld + col];
  *   v *= (mask[row*mask_ld+col] != 0) ? mask_scale : 0;  v += residual[row*res_ld+col];
  *   out_f32[row*out_f32_ld+col] = v;  out_act[row*out_act_ld+col] = v (hi[/lo] bf16).
  * NULL pointers skip their step. */
 typedef struct dsvg_epilogue {
+  const float* acc_scale_dev; /* optional DEVICE scalar (upstream autograd gradient x loss weight) */
   const float* bias;
   int scale_cols;
   float scale;
@@ -69,12 +70,93 @@ typedef struct dsvg_epilogue {
 int dsvg_linear(const dsvg_bf16* X, size_t x_lo_off, int lda, const dsvg_bf16* W, size_t w_lo_off, int ldb, int M,
                 int N, int K, const dsvg_epilogue* ep, void* stream);
 
-/* C[P,Q] (+)= alpha * A[M,P]^T . B[M,Q]   (contraction over the M rows; A, B row-major act tensors).
- * accumulate != 0: fp32 atomic add into C (split over M across CTAs), else C must be zero-filled by the caller
- * when more than one split is used -- the library always adds.  Weight gradients of every F.linear above
- * (autograd of the reference, loss.backward() at train.py:98). */
+/* C[P,Q] += alpha * (*alpha_dev) * A[M,P]^T . B[M,Q]   (contraction over the M rows; A, B row-major act tensors;
+ * alpha_dev optional DEVICE scalar).  fp32 atomic adds into C (the M range is split across CTAs), so C is the
+ * gradient accumulator itself.  Weight gradients of every F.linear above (autograd of the reference,
+ * loss.backward() at train.py:98). */
 int dsvg_outer(const dsvg_bf16* A, size_t a_lo_off, int lda, const dsvg_bf16* B, size_t b_lo_off, int ldb, int M,
-               int P, int Q, float alpha, float* C, int ldc, void* stream);
+               int P, int Q, float alpha, const float* alpha_dev, float* C, int ldc, void* stream);
+
+/* ---- sequence bookkeeping (model/utils.py:7-66) ------------------------------------------------------ */
+/* From commands[nseq, L] (ids stored as float): first_eos[nseq], visible[nseq] (#EOS < L-1), key_valid[nseq*L]
+ * (1 before the first EOS), grp[nseq*L] (# of "m" so far), counts[2] += {loss_cmd positions, loss_args slots}.
+ * Any output pointer may be NULL. */
+int dsvg_seq_prep(const float* commands, int nseq, int L, int* first_eos, uint8_t* visible, uint8_t* key_valid,
+                  uint8_t* grp, float* counts, void* stream);
+
+/* ---- embeddings (model.py:46-57, 70-73; positional_encoding.py:40-43) -------------------------------- */
+/* table[k*V+v] = arg_embed[v] . W[:, 64k:64k+64]^T, stored as differences to row v=0 (v>=1); base = bias + sum_k row0 */
+int dsvg_embed_fold(const float* arg_embed, const float* W, const float* bias, float* table, float* base, int V,
+                    int n_args, int d, void* stream);
+/* x[t] = dropout(base + cmd_tab[cmd] + pos_tab[t % L] (+ grp_tab[grp[t]]) + sum_{k: arg_k != -1} table[k*V+arg_k+1]) */
+int dsvg_embed_fwd(const float* commands, const float* args, const uint8_t* grp, const float* cmd_tab,
+                   const float* table, const float* base, const float* pos_tab, const float* grp_tab, float* x, int T,
+                   int L, int V, int n_args, int d, float drop_p, uint32_t drop_site, uint64_t seed, void* stream);
+/* all embedding-parameter gradients from dx (accumulating); scratch_table: n_args*V*d floats of workspace */
+int dsvg_embed_bwd(const float* commands, const float* args, const uint8_t* grp, const float* dx,
+                   const float* arg_embed, const float* W, float* d_cmd_tab, float* d_pos_tab, float* d_grp_tab,
+                   float* d_arg_embed, float* d_W, float* d_bias, float* scratch_table, int nseq, int L, int V,
+                   int n_args, int d, int n_grp, float drop_p, uint32_t drop_site, uint64_t seed, void* stream);
+/* x[r] = dropout(add[r] + tab[r % L]) (add may be NULL: ConstEmbedding) and its backward */
+int dsvg_rows_embed_fwd(const float* add, const float* tab, float* x, int R, int L, int d, float drop_p,
+                        uint32_t drop_site, uint64_t seed, void* stream);
+int dsvg_rows_embed_bwd(const float* dx, float* dadd, float* dtab, int nseq, int L, int d, float drop_p,
+                        uint32_t drop_site, uint64_t seed, void* stream);
+
+/* ---- LayerNorm (+ masked mean over the sequence: model.py:137,161) ------------------------------------ */
+int dsvg_ln_fwd(const float* x, const float* gamma, const float* beta, dsvg_bf16* y, size_t y_lo_off, float* mean,
+                float* rstd, int M, int D, void* stream);
+int dsvg_ln_pool_fwd(const float* x, const float* gamma, const float* beta, const uint8_t* valid, float* z,
+                     float* mean, float* rstd, float* inv_cnt, int nseq, int L, int D, void* stream);
+/* dy from an act tensor, or (dz != NULL) dy[r] = dz[r / L] * valid[r] * inv_cnt[r / L].  dx_out = dx_in + LN'(dy);
+ * dact = dropout_mask * dx_out as act; dgamma/dbeta accumulate. */
+int dsvg_ln_bwd(const float* x, const float* mean, const float* rstd, const float* gamma, const dsvg_bf16* dy,
+                size_t dy_lo_off, const float* dz, const uint8_t* valid, const float* inv_cnt, int L,
+                const float* dx_in, float* dx_out, dsvg_bf16* dact, size_t dact_lo_off, float drop_p,
+                uint32_t drop_site, uint64_t seed, float* dgamma, float* dbeta, int M, int D, void* stream);
+
+/* ---- self-attention over short sequences (functional.py:168-248) -------------------------------------- */
+int dsvg_attn_fwd(const dsvg_bf16* qkv, size_t qkv_lo_off, const uint8_t* key_valid, dsvg_bf16* out, size_t out_lo_off,
+                  int nseq, int L, int H, int head_dim, float drop_p, uint32_t drop_site, uint64_t seed, void* stream);
+int dsvg_attn_bwd(const dsvg_bf16* qkv, size_t qkv_lo_off, const uint8_t* key_valid, const dsvg_bf16* dout,
+                  size_t dout_lo_off, dsvg_bf16* dqkv, size_t dqkv_lo_off, int nseq, int L, int H, int head_dim,
+                  float q_scale, float drop_p, uint32_t drop_site, uint64_t seed, void* stream);
+
+/* ---- SVGLoss (model/loss.py:19-65): loss sums + unit-scale d(loss)/d(logits) --------------------------- */
+int dsvg_ce_args(const float* logits, int ld_logits, const float* commands, const float* args, const float* counts,
+                 dsvg_bf16* dlogits, size_t dl_lo_off, int ld_dl, float* acc, int nseq, int L, int n_args,
+                 int n_classes, void* stream);
+int dsvg_ce_cmd(const float* logits, const float* commands, const int* first_eos, const uint8_t* visible,
+                const float* counts, dsvg_bf16* dlogits, size_t dl_lo_off, int ld_dl, float* acc, int nseq, int L,
+                int n_classes, void* stream);
+int dsvg_ce_vis(const float* logits, const uint8_t* visible, dsvg_bf16* dlogits, size_t dl_lo_off, int ld_dl,
+                float* acc, int nseq, float inv_total, void* stream);
+int dsvg_kl_sum(const float* mu, const float* logsigma, float* acc, int n, void* stream);
+/* out[0..4] = loss, loss_cmd, loss_args, loss_visibility, loss_kl; out[5] = 1 if the KL clamp passes gradient */
+int dsvg_loss_finalize(const float* acc, const float* counts, float* out, float w_cmd, float w_args, float w_vis,
+                       float w_kl, float kl_tolerance, float inv_vis_total, float inv_kl_total, int has_vis,
+                       int has_kl, void* stream);
+/* VAE reparameterisation (model.py:182-187) */
+int dsvg_vae_fwd(const float* mu, const float* logsigma, const float* eps, float* z, int n, void* stream);
+int dsvg_vae_bwd(const float* mu, const float* logsigma, const float* eps, const float* dz, const float* kl_coef_dev,
+                 const float* loss_out, float inv_total, float* dmu, float* dls, int n, void* stream);
+
+/* ---- helpers -------------------------------------------------------------------------------------------- */
+/* fp32 -> act cast (optional transposed copy, optional (mask != 0) * mask_scale, optional dropout) */
+int dsvg_cast_act(const float* in, int ld_in, int R, int C, dsvg_bf16* out, size_t out_lo_off, int ld_out,
+                  dsvg_bf16* outT, size_t outT_lo_off, int ld_t, const dsvg_bf16* mask, size_t mask_lo_off,
+                  int ld_mask, float mask_scale, float drop_p, uint32_t drop_site, uint64_t seed, void* stream);
+/* dst[c] += (*alpha_dev) * sum_r a[r, c]  (bias gradients) */
+int dsvg_colsum(const dsvg_bf16* a, size_t lo_off, int ld, int M, int N, const float* alpha_dev, float* dst,
+                void* stream);
+/* out[q] = dropout(sum_{s<L} in[q*L+s])  (backward of the linear_global broadcast, improved_transformer.py:131-136) */
+int dsvg_seg_sum(const float* in, int nseq, int L, int d, dsvg_bf16* out, size_t out_lo_off, float* out_f32,
+                 float drop_p, uint32_t drop_site, uint64_t seed, void* stream);
+/* LabelEmbedding (model.py:87-89) gather and its gradient scatter-add */
+int dsvg_gather_rows(const float* table, const long long* idx, int n, int w, dsvg_bf16* out, size_t out_lo_off,
+                     void* stream);
+int dsvg_scatter_rows(const float* g, const long long* idx, int n, int w, float* dtable, void* stream);
+int dsvg_add_f32(const float* a, const float* b, float* y, size_t n, void* stream);
 
 #ifdef __cplusplus
 }
