@@ -690,7 +690,7 @@ extern "C" int dsvg_linear(const dsvg_bf16* X, size_t x_lo_off, int lda, const d
                            int M, int N, int K, const dsvg_epilogue* e, void* stream) {
   DSVG_CHECK(X && W && e, "dsvg_linear: null pointer");
   DSVG_CHECK(M > 0 && N > 0 && K > 0, "dsvg_linear: bad shape %d x %d x %d", M, N, K);
-  DSVG_CHECK(K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0, "dsvg_linear: K/lda/ldb must be multiples of 8");
+  DSVG_CHECK(lda % 8 == 0 && ldb % 8 == 0, "dsvg_linear: lda/ldb must be multiples of 8 elements (TMA row stride)");
   DSVG_CHECK((x_lo_off == 0) == (w_lo_off == 0), "dsvg_linear: both operands must have the same number of planes");
   Epi ep{};
   ep.acc_scale_dev = e->acc_scale_dev;

@@ -1,0 +1,843 @@
+"""`SVGTransformer`: drop-in for deepsvg.model.model.SVGTransformer (model.py:288-412) on the accelerated path.
+
+Same constructor (`SVGTransformer(model_cfg)`), forward signature, result-dict keys and `state_dict` names/shapes as the
+reference, so `deepsvg/train.py` runs unchanged.  Parameters are ordinary fp32 `nn.Parameter`s; the
+arithmetic is one `torch.autograd.Function` whose forward and backward are sequences of libdsvg_b200 kernel launches
+(tcgen05 GEMMs, fused LayerNorm / attention / embedding / loss kernels) on torch's current CUDA stream.  There is no
+CPU or eager-PyTorch fallback: without the CUDA library, or with CPU tensors, forward raises.
+
+Internal layout is token-major `(icon n, path g, position s)` -- the reference's `_make_seq_first` / `_pack_group_batch`
+permutations (utils/utils.py:20-49) never happen; logits land directly at `[n, g, s, ...]`.
+
+Precision: "bf16" (fast: single-plane bf16 operands, fp32 accumulate) or "bf16x3" (parity: split hi/lo operands, three
+tensor-core products per K step, ~fp32 accuracy on the same kernels).  Select with `SVGTransformer(cfg, precision=...)`
+or env DSVG_PRECISION.
+"""
+import math
+import os
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .config import check_supported
+from .ops import Act
+
+CMD_ARGS_MASK = torch.tensor([[0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1],   # m      (difflib/tensor.py:15-21)
+                              [0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1],   # l
+                              [0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1],   # c
+                              [1, 1, 1, 1, 1, 0, 0, 0, 0, 1, 1],   # a
+                              [0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0],   # EOS
+                              [0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0],   # SOS
+                              [0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0]])  # z
+
+
+def _r8(n):
+    return (n + 7) // 8 * 8
+
+
+# ======================================================================================================
+# parameter inventory (names / shapes / initialisers of the reference module tree)
+# ======================================================================================================
+def _param_specs(cfg):
+    """[(name, shape, init kind)] in the reference's registration order.  init kinds:
+    kaiming (model.py:38-44), xavier (attention.py:85-95), linw/linb (nn.Linear defaults), zeros, ones, vae."""
+    d, dz, ff = cfg.d_model, cfg.dim_z, cfg.dim_feedforward
+    two = cfg.encode_stages == 2
+    S = []
+
+    def lin(n, o, i):
+        S.append((n + ".weight", (o, i), "linw"))
+        S.append((n + ".bias", (o,), "linb:%d" % i))
+
+    def ln(n):
+        S.append((n + ".weight", (d,), "ones"))
+        S.append((n + ".bias", (d,), "zeros"))
+
+    def layer(p, glob):
+        S.append((p + ".self_attn.in_proj_weight", (3 * d, d), "xavier"))
+        S.append((p + ".self_attn.in_proj_bias", (3 * d,), "zeros"))
+        S.append((p + ".self_attn.out_proj.weight", (d, d), "linw"))
+        S.append((p + ".self_attn.out_proj.bias", (d,), "zeros"))
+        if glob:
+            lin(p + ".linear_global", d, dz)
+        if cfg.label_condition:
+            lin(p + ".linear_global2", d, cfg.dim_label)
+        lin(p + ".linear1", ff, d)
+        lin(p + ".linear2", d, ff)
+        ln(p + ".norm1")
+        ln(p + ".norm2")
+
+    def stack(p, n, glob):
+        for i in range(n):
+            layer("%s.layers.%d" % (p, i), glob)
+        ln(p + ".norm")
+
+    enc_len = cfg.max_seq_len if two else cfg.max_total_len
+    S.append(("encoder.embedding.command_embed.weight", (cfg.n_commands, d), "kaiming"))
+    S.append(("encoder.embedding.arg_embed.weight", (cfg.args_dim + 1, 64), "kaiming"))
+    S.append(("encoder.embedding.embed_fcn.weight", (d, 64 * cfg.n_args), "kaiming"))
+    S.append(("encoder.embedding.embed_fcn.bias", (d,), "linb:%d" % (64 * cfg.n_args)))
+    if not two:
+        S.append(("encoder.embedding.group_embed.weight", (cfg.max_num_groups + 2, d), "kaiming"))
+    S.append(("encoder.embedding.pos_encoding.pos_embed.weight", (enc_len + 2, d), "kaiming"))
+    if cfg.label_condition:
+        S.append(("encoder.label_embedding.label_embedding.weight", (cfg.n_labels, cfg.dim_label), "kaiming"))
+    stack("encoder.encoder", cfg.n_layers, False)
+    if two:
+        S.append(("encoder.hierarchical_PE.pos_embed.weight", (cfg.max_num_groups, d), "kaiming"))
+        stack("encoder.hierarchical_encoder", cfg.n_layers, False)
+    if cfg.use_resnet:
+        for i in range(1, 5):
+            lin("resnet.linear%d.0" % i, d, d)
+    if cfg.use_vae:
+        for n in ("vae.enc_mu_fcn", "vae.enc_sigma_fcn"):
+            S.append((n + ".weight", (dz, d), "vae"))
+            S.append((n + ".bias", (dz,), "zeros"))
+    else:
+        lin("bottleneck.bottleneck", dz, d)
+    if cfg.label_condition:
+        S.append(("decoder.label_embedding.label_embedding.weight", (cfg.n_labels, cfg.dim_label), "kaiming"))
+    if two:
+        S.append(("decoder.hierarchical_embedding.PE.pos_embed.weight", (cfg.num_groups_proposal, d), "kaiming"))
+        stack("decoder.hierarchical_decoder", cfg.n_layers_decode, True)
+        lin("decoder.hierarchical_fcn.visibility_fcn", 2, d)
+        lin("decoder.hierarchical_fcn.z_fcn", dz, d)
+    dec_len = (cfg.max_seq_len if two else cfg.max_total_len) + 1
+    S.append(("decoder.embedding.PE.pos_embed.weight", (dec_len, d), "kaiming"))
+    stack("decoder.decoder", cfg.n_layers_decode, True)
+    lin("decoder.fcn.command_fcn", cfg.n_commands, d)
+    lin("decoder.fcn.args_fcn", cfg.n_args * (cfg.args_dim + 1), d)
+    return S
+
+
+def _init_tensor(shape, kind):
+    t = torch.empty(*shape)
+    if kind == "kaiming":
+        nn.init.kaiming_normal_(t, mode="fan_in")
+    elif kind == "xavier":
+        nn.init.xavier_uniform_(t)
+    elif kind == "linw":
+        nn.init.kaiming_uniform_(t, a=math.sqrt(5))
+    elif kind.startswith("linb:"):
+        b = 1.0 / math.sqrt(int(kind[5:]))
+        nn.init.uniform_(t, -b, b)
+    elif kind == "zeros":
+        t.zero_()
+    elif kind == "ones":
+        t.fill_(1.0)
+    elif kind == "vae":
+        nn.init.normal_(t, std=0.001)
+    else:
+        raise ValueError(kind)
+    return t
+
+
+class _Node(nn.Module):
+    """Anonymous container used to reproduce the reference's dotted parameter paths."""
+
+
+def _register(root, dotted, tensor, is_buffer=False):
+    parts = dotted.split(".")
+    m = root
+    for p in parts[:-1]:
+        if p not in m._modules:
+            m.add_module(p, _Node())
+        m = m._modules[p]
+    if is_buffer:
+        m.register_buffer(parts[-1], tensor)
+    else:
+        m.register_parameter(parts[-1], nn.Parameter(tensor))
+
+
+# ======================================================================================================
+# saved state of one forward call
+# ======================================================================================================
+class _Saved:
+    """Everything the backward pass (and the fused loss) needs; one instance per forward call."""
+
+    def __init__(self):
+        self.layers = {}
+        self.t = {}
+
+
+class LossHandle:
+    """Side channel between SVGTransformer's autograd node and SVGLoss (attached to the logits tensors).
+    The loss kernels leave unit-scale d(loss)/d(logits) in `dl_*` (act tensors) and the per-term upstream scales in
+    `scales` (device float[4]: args, cmd, visibility, kl); the model's backward consumes them directly."""
+
+    def __init__(self, saved, token):
+        self.saved, self.token = saved, token
+        self.dl_args = self.dl_cmd = self.dl_vis = None
+        self.scales = None
+        self.loss_out = None
+        self.used = False
+
+
+class _SVGFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, inputs, token, *params):
+        ctx.set_materialize_grads(False)
+        outs, saved = model._forward_impl(inputs)
+        ctx.model, ctx.saved = model, saved
+        saved.token = token
+        ctx.n_outs = len(outs)
+        return tuple(outs) + (token.detach().clone(),)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        model, saved = ctx.model, ctx.saved
+        flat = model._backward_impl(saved, grads[:-1], grads[-1])
+        return (None, None, None) + tuple(flat)
+
+
+# ======================================================================================================
+class SVGTransformer(nn.Module):
+    def __init__(self, cfg, precision=None, process_group=None):
+        super().__init__()
+        check_supported(cfg)
+        self.cfg = cfg
+        self.args_dim = cfg.args_dim + 1                      # model.py:293 (rel_targets unsupported)
+        self.precision = precision or os.environ.get("DSVG_PRECISION", "bf16")
+        if self.precision not in ("bf16", "bf16x3"):
+            raise ValueError("precision must be 'bf16' or 'bf16x3'")
+        self.process_group = process_group                    # set => gradients are all-reduced (SUM) in backward
+        self._specs = _param_specs(cfg)
+        two = cfg.encode_stages == 2
+        first_layer = {}
+        for name, shape, kind in self._specs:
+            t = _init_tensor(shape, kind)
+            # transformer.py:383-384: _get_clones deep-copies => all layers of a stack start identical
+            if ".layers." in name:
+                stack, rest = name.split(".layers.")
+                idx, leaf = rest.split(".", 1)
+                key = stack + "|" + leaf
+                if idx == "0":
+                    first_layer[key] = t
+                else:
+                    t = first_layer[key].clone()
+            _register(self, name, t)
+        enc_len = (cfg.max_seq_len if two else cfg.max_total_len) + 2
+        dec_len = (cfg.max_seq_len if two else cfg.max_total_len) + 1
+        pos = lambda n: torch.arange(0, n, dtype=torch.long).unsqueeze(1)   # positional_encoding.py:30-31
+        _register(self, "encoder.embedding.pos_encoding.position", pos(enc_len), True)
+        if two:
+            _register(self, "encoder.hierarchical_PE.position", pos(cfg.max_num_groups), True)
+            _register(self, "decoder.hierarchical_embedding.PE.position", pos(cfg.num_groups_proposal), True)
+        _register(self, "decoder.embedding.PE.position", pos(dec_len), True)
+        self.register_buffer("cmd_args_mask", CMD_ARGS_MASK.clone())       # model.py:309
+        self._pnames = [n for n, _, _ in self._specs]
+        self._sites = {}
+        self._wcache = {}
+        self._eps_override = None      # tests inject the VAE noise here (SURVEY.md 8c hazard 2)
+
+    # -------------------------------------------------------------------------------------------------
+    def _param(self, name):
+        m = self
+        for p in name.split("."):
+            m = m._modules[p] if p in m._modules else m._parameters[p]
+        return m
+
+    def _pdict(self):
+        return {n: self._param(n) for n in self._pnames}
+
+    def _site(self, tag):
+        if tag not in self._sites:
+            self._sites[tag] = len(self._sites) + 1
+        return self._sites[tag]
+
+    @property
+    def planes(self):
+        return 2 if self.precision == "bf16x3" else 1
+
+    # -------------------------------------------------------------------------------------------------
+    def forward(self, commands_enc, args_enc, commands_dec, args_dec, label=None, z=None, hierarch_logits=None,
+                return_tgt=True, params=None, encode_mode=False, return_hierarch=False):
+        """model.py:352-412.  Tensors are batch-first float32 CUDA tensors: commands (N, G, S+2), args (N, G, S+2, 11)."""
+        cfg = self.cfg
+        if hierarch_logits is not None:
+            raise NotImplementedError("deepsvg_b200: forward(hierarch_logits=...) is not on the accelerated path")
+        if z is None and (commands_enc is None or args_enc is None):
+            raise ValueError("encoder inputs are required when z is not given")
+        ref = commands_enc if commands_enc is not None else z
+        if not ref.is_cuda:
+            raise RuntimeError("deepsvg_b200 has no CPU path: inputs and parameters must live on a CUDA device")
+        if cfg.label_condition and label is None:
+            raise ValueError("label_condition=True needs `label`")
+        inputs = dict(commands=commands_enc, args=args_enc, label=label, z=z, encode_mode=encode_mode,
+                      return_hierarch=return_hierarch, training=self.training)
+        plist = [self._param(n) for n in self._pnames]
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in plist)
+        token = torch.zeros((), device=ref.device, requires_grad=need_grad)
+        need_grad = need_grad and not return_hierarch          # return_hierarch is an inference-only exit
+        if need_grad:
+            outs = _SVGFunction.apply(self, inputs, token, *plist)
+            outs, tok_out = outs[:-1], outs[-1]
+        else:
+            with torch.no_grad():
+                outs, _ = self._forward_impl(inputs)
+            tok_out = None
+        saved = self._last_saved
+        N = ref.shape[0]
+        if encode_mode:
+            return outs[0].view(1, 1, N, cfg.dim_z)            # seq-first like model.py:371 (reference quirk, 3.4)
+        two = cfg.decode_stages == 2
+        if return_hierarch:
+            Gp = cfg.num_groups_proposal
+            return outs[0].view(N, Gp, 2).permute(1, 0, 2).unsqueeze(0), outs[1].view(N, Gp, -1).permute(1, 0, 2).unsqueeze(0)
+        G = cfg.num_groups_proposal if two else 1
+        Ld = (cfg.max_seq_len if two else cfg.max_total_len) + 1
+        it = iter(outs)
+        res = {"command_logits": next(it).view(N, G, Ld, cfg.n_commands),
+               "args_logits": next(it).view(N, G, Ld, cfg.n_args, self.args_dim)}
+        if two:
+            res["visibility_logits"] = next(it).view(N, G, 1, 2)
+        if return_tgt:
+            res["tgt_commands"] = commands_dec
+            res["tgt_args"] = args_dec
+            if cfg.use_vae and z is None:
+                res["mu"] = next(it).view(N, 1, 1, cfg.dim_z)
+                res["logsigma"] = next(it).view(N, 1, 1, cfg.dim_z)
+        if tok_out is not None:
+            handle = LossHandle(saved, tok_out)
+            handle.planes, handle.process_group = self.planes, self.process_group
+            saved.handle = handle
+            for k in ("command_logits", "args_logits"):
+                res[k]._dsvg_handle = handle
+        return res
+
+    # =================================================================================================
+    # weights: fp32 master -> (split-)bf16 operand + transposed operand, refreshed when the parameter changes
+    # =================================================================================================
+    def _pack(self, name, need_t=True):
+        p = self._param(name)
+        key = (p.data_ptr(), p._version, self.planes, p.device)
+        hit = self._wcache.get(name)
+        if hit is not None and hit[0] == key:
+            return hit[1], hit[2]
+        Nn, K = p.shape
+        if hit is not None and hit[1].planes == self.planes and hit[1].t.device == p.device:
+            w, wt = hit[1], hit[2]
+        else:
+            w = Act(Nn, K, self.planes, p.device, ld=_r8(K), zero=True)
+            wt = Act(K, Nn, self.planes, p.device, ld=_r8(Nn), zero=True)
+        ops.cast_act(p.data, Nn, K, out=w, outT=wt)
+        self._wcache[name] = (key, w, wt)
+        return w, wt
+
+    # =================================================================================================
+    # forward
+    # =================================================================================================
+    def _drop(self, sv, tag, p=None):
+        """(p, site, seed) of a dropout call site; p = 0 in eval mode."""
+        if not sv.training:
+            return (0.0, 0, 0)
+        return (self.cfg.dropout if p is None else p, self._site(tag), sv.seed)
+
+    def _layer_fwd(self, sv, pre, x, M, L, nseq, key_valid, rowvec, rpg):
+        cfg = self.cfg
+        d, ff, H = cfg.d_model, cfg.dim_feedforward, cfg.n_heads
+        hd = d // H
+        dev, pl = x.device, self.planes
+        P = lambda n: self._param(pre + "." + n)
+        s = {}
+        a = Act(M, d, pl, dev)
+        s["mean1"], s["rstd1"] = torch.empty(M, device=dev), torch.empty(M, device=dev)
+        ops.ln_fwd(x, P("norm1.weight"), P("norm1.bias"), a, s["mean1"], s["rstd1"], M, d)
+        qkv = Act(M, 3 * d, pl, dev)
+        w_in, _ = self._pack(pre + ".self_attn.in_proj_weight")
+        ops.linear(a, w_in, M, 3 * d, d, bias=P("self_attn.in_proj_bias"), scale_cols=d, scale=float(hd) ** -0.5,
+                   out_act=qkv)
+        o = Act(M, d, pl, dev)
+        ops.attn_fwd(qkv, key_valid, o, nseq, L, H, hd, self._drop(sv, pre + ".attn"))
+        x1 = torch.empty(M, d, device=dev)
+        w_o, _ = self._pack(pre + ".self_attn.out_proj.weight")
+        ops.linear(o, w_o, M, d, d, bias=P("self_attn.out_proj.bias"), drop=self._drop(sv, pre + ".drop1"),
+                   rowvec=rowvec, rows_per_group=rpg, residual=x, out_f32=x1)
+        b = Act(M, d, pl, dev)
+        s["mean2"], s["rstd2"] = torch.empty(M, device=dev), torch.empty(M, device=dev)
+        ops.ln_fwd(x1, P("norm2.weight"), P("norm2.bias"), b, s["mean2"], s["rstd2"], M, d)
+        h = Act(M, ff, pl, dev)
+        w1, _ = self._pack(pre + ".linear1.weight")
+        ops.linear(b, w1, M, ff, d, bias=P("linear1.bias"), relu=True, drop=self._drop(sv, pre + ".dropff"), out_act=h)
+        x2 = torch.empty(M, d, device=dev)
+        w2, _ = self._pack(pre + ".linear2.weight")
+        ops.linear(h, w2, M, d, ff, bias=P("linear2.bias"), drop=self._drop(sv, pre + ".drop2"), residual=x1,
+                   out_f32=x2)
+        s.update(x=x, a=a, qkv=qkv, o=o, x1=x1, b=b, h=h)
+        sv.layers[pre] = s
+        return x2
+
+    def _globals_fwd(self, sv, pre, zmem, n_groups, lab, lab_rpg):
+        """rowvec of a layer: dropout(linear_global(zmem)) [+ dropout(linear_global2(label))]
+        (improved_transformer.py:47-49,131-136).  zmem: Act [n_groups, dz] or None; lab: Act [N, dim_label] or None.
+        lab_rpg: how many zmem groups share one label row (1 when both are per icon)."""
+        cfg = self.cfg
+        d = cfg.d_model
+        g2 = None
+        if lab is not None:
+            N = lab.rows
+            g2 = torch.empty(N, d, device=lab.t.device)
+            w, _ = self._pack(pre + ".linear_global2.weight")
+            ops.linear(lab, w, N, d, cfg.dim_label, bias=self._param(pre + ".linear_global2.bias"),
+                       drop=self._drop(sv, pre + ".dropg2"), out_f32=g2)
+        if zmem is None:
+            return g2
+        g = torch.empty(n_groups, d, device=zmem.t.device)
+        w, _ = self._pack(pre + ".linear_global.weight")
+        ops.linear(zmem, w, n_groups, d, cfg.dim_z, bias=self._param(pre + ".linear_global.bias"),
+                   drop=self._drop(sv, pre + ".dropg"), rowvec=g2, rows_per_group=lab_rpg, out_f32=g)
+        return g
+
+    def _stack_fwd(self, sv, pre, n_layers, x, M, L, nseq, key_valid, zmem=None, lab=None, lab_rows_per_group=1,
+                   lab_rpg=1):
+        """L = sequence length; rows of one rowvec group = L (zmem per sequence) or lab_rows_per_group (label only)."""
+        for i in range(n_layers):
+            lp = "%s.layers.%d" % (pre, i)
+            rv = self._globals_fwd(sv, lp, zmem, nseq, lab, lab_rpg) if (zmem is not None or lab is not None) else None
+            rpg = L if zmem is not None else lab_rows_per_group
+            x = self._layer_fwd(sv, lp, x, M, L, nseq, key_valid, rv, rpg)
+        return x
+
+    def _forward_impl(self, inp):
+        cfg = self.cfg
+        sv = _Saved()
+        self._last_saved = sv
+        sv.training = bool(inp["training"])
+        sv.seed = int(torch.empty((), dtype=torch.int64).random_().item()) if sv.training else 0
+        d, dz = cfg.d_model, cfg.dim_z
+        two = cfg.encode_stages == 2
+        pl = self.planes
+        P = self._param
+        commands, args, label = inp["commands"], inp["args"], inp["label"]
+        sv.label = label
+        sv.has_encoder = inp["z"] is None
+        if sv.has_encoder:
+            dev = commands.device
+            commands = commands.contiguous().float()
+            args = args.contiguous().float()
+            N, G, L = commands.shape
+            if two and G != cfg.max_num_groups:
+                raise ValueError("two-stage model expects %d paths per icon, got %d" % (cfg.max_num_groups, G))
+            if not two and G != 1:
+                raise ValueError("one-stage model expects grouped tensors with G = 1")
+            exp_L = (cfg.max_seq_len if two else cfg.max_total_len) + 2
+            if L != exp_L:
+                raise ValueError("expected %d positions per sequence, got %d" % (exp_L, L))
+            nseq, M1 = N * G, N * G * L
+            sv.commands, sv.args, sv.N, sv.G, sv.L = commands, args, N, G, L
+            # ---- bookkeeping (model/utils.py) ----
+            sv.first_eos = torch.empty(nseq, dtype=torch.int32, device=dev)
+            sv.visible = torch.empty(nseq, dtype=torch.uint8, device=dev)
+            sv.key_valid = torch.empty(M1, dtype=torch.uint8, device=dev)
+            sv.grp = torch.empty(M1, dtype=torch.uint8, device=dev) if not two else None
+            sv.counts = torch.zeros(2, device=dev)
+            ops.seq_prep(commands, nseq, L, sv.first_eos, sv.visible, sv.key_valid, sv.grp, sv.counts)
+            # ---- embedding (model.py:46-57) ----
+            V, na = cfg.args_dim + 1, cfg.n_args
+            sv.table = torch.empty(na * V, d, device=dev)
+            sv.base = torch.empty(d, device=dev)
+            ops.embed_fold(P("encoder.embedding.arg_embed.weight"), P("encoder.embedding.embed_fcn.weight"),
+                           P("encoder.embedding.embed_fcn.bias"), sv.table, sv.base, V, na, d)
+            x = torch.empty(M1, d, device=dev)
+            ops.embed_fwd(commands, args, sv.grp, P("encoder.embedding.command_embed.weight"), sv.table, sv.base,
+                          P("encoder.embedding.pos_encoding.pos_embed.weight"),
+                          None if two else P("encoder.embedding.group_embed.weight"), x, M1, L, V, na, d,
+                          self._drop(sv, "enc.pe", 0.1))                       # positional_encoding.py:26 (p fixed)
+            lab_e = None
+            if cfg.label_condition:
+                lab_e = Act(N, cfg.dim_label, pl, dev)
+                ops.gather_rows(P("encoder.label_embedding.label_embedding.weight"), label, N, cfg.dim_label, lab_e)
+            sv.lab_e = lab_e
+            # ---- E1 (model.py:135-137) ----
+            x = self._stack_fwd(sv, "encoder.encoder", cfg.n_layers, x, M1, L, nseq, sv.key_valid, lab=lab_e,
+                                lab_rows_per_group=G * L)
+            sv.e1_x = x
+            zp = torch.empty(nseq, d, device=dev)
+            sv.e1_mean, sv.e1_rstd = torch.empty(M1, device=dev), torch.empty(M1, device=dev)
+            sv.e1_icnt = torch.empty(nseq, device=dev)
+            ops.ln_pool_fwd(x, P("encoder.encoder.norm.weight"), P("encoder.encoder.norm.bias"), sv.key_valid, zp,
+                            sv.e1_mean, sv.e1_rstd, sv.e1_icnt, nseq, L, d)
+            if two:
+                # ---- E2 (model.py:153-162): sequences of G path codes per icon ----
+                x = torch.empty(nseq, d, device=dev)
+                ops.rows_embed_fwd(zp, P("encoder.hierarchical_PE.pos_embed.weight"), x, nseq, G, d,
+                                   self._drop(sv, "enc.pe2", 0.1))
+                x = self._stack_fwd(sv, "encoder.hierarchical_encoder", cfg.n_layers, x, nseq, G, N, sv.visible,
+                                    lab=lab_e, lab_rows_per_group=G)
+                sv.e2_x = x
+                z = torch.empty(N, d, device=dev)
+                sv.e2_mean, sv.e2_rstd = torch.empty(nseq, device=dev), torch.empty(nseq, device=dev)
+                sv.e2_icnt = torch.empty(N, device=dev)
+                ops.ln_pool_fwd(x, P("encoder.hierarchical_encoder.norm.weight"),
+                                P("encoder.hierarchical_encoder.norm.bias"), sv.visible, z, sv.e2_mean, sv.e2_rstd,
+                                sv.e2_icnt, N, G, d)
+            else:
+                z = zp
+            # ---- ResNet (basic_blocks.py:59-65) ----
+            sv.res = []
+            if cfg.use_resnet:
+                for i in range(1, 5):
+                    za = Act(N, d, pl, dev)
+                    ops.cast_act(z, N, d, out=za)
+                    r32, ra = torch.empty(N, d, device=dev), Act(N, d, pl, dev)
+                    w, _ = self._pack("resnet.linear%d.0.weight" % i)
+                    ops.linear(za, w, N, d, d, bias=P("resnet.linear%d.0.bias" % i), relu=True, out_f32=r32, out_act=ra)
+                    zn = torch.empty(N, d, device=dev)
+                    ops.add_f32(z, r32, zn)
+                    sv.res.append((za, ra))
+                    z = zn
+            za = Act(N, d, pl, dev)
+            ops.cast_act(z, N, d, out=za)
+            sv.lat_in = za
+            zl = torch.empty(N, dz, device=dev)
+            z_act = Act(N, dz, pl, dev)
+            if cfg.use_vae:                                                    # model.py:182-187
+                sv.mu, sv.ls = torch.empty(N, dz, device=dev), torch.empty(N, dz, device=dev)
+                w, _ = self._pack("vae.enc_mu_fcn.weight")
+                ops.linear(za, w, N, dz, d, bias=P("vae.enc_mu_fcn.bias"), out_f32=sv.mu)
+                w, _ = self._pack("vae.enc_sigma_fcn.weight")
+                ops.linear(za, w, N, dz, d, bias=P("vae.enc_sigma_fcn.bias"), out_f32=sv.ls)
+                sv.eps = self._eps_override if self._eps_override is not None else torch.randn(N, dz, device=dev)
+                ops.vae_fwd(sv.mu, sv.ls, sv.eps, zl, N * dz)
+                ops.cast_act(zl, N, dz, out=z_act)
+            else:                                                              # model.py:196-197
+                w, _ = self._pack("bottleneck.bottleneck.weight")
+                ops.linear(za, w, N, dz, d, bias=P("bottleneck.bottleneck.bias"), out_f32=zl, out_act=z_act)
+        else:
+            zin = inp["z"]
+            N = zin.shape[0]
+            dev = zin.device
+            zl = zin.reshape(N, dz).contiguous().float()                        # batch-first (N,1,1,dz), model.py:369
+            z_act = Act(N, dz, pl, dev)
+            ops.cast_act(zl, N, dz, out=z_act)
+            sv.N = N
+        sv.z32, sv.z_act = zl, z_act
+        if inp["encode_mode"]:
+            return [zl], sv
+
+        # ---- decoder (model.py:243-285) ----
+        lab_d = None
+        if cfg.label_condition:
+            lab_d = Act(N, cfg.dim_label, pl, dev)
+            ops.gather_rows(P("decoder.label_embedding.label_embedding.weight"), label, N, cfg.dim_label, lab_d)
+        sv.lab_d = lab_d
+        outs = []
+        if two:
+            Gp = cfg.num_groups_proposal
+            nq = N * Gp
+            x = torch.empty(nq, d, device=dev)
+            ops.rows_embed_fwd(None, P("decoder.hierarchical_embedding.PE.pos_embed.weight"), x, nq, Gp, d,
+                               self._drop(sv, "dec.pe2", 0.1))
+            x = self._stack_fwd(sv, "decoder.hierarchical_decoder", cfg.n_layers_decode, x, nq, Gp, N, None,
+                                zmem=z_act, lab=lab_d, lab_rpg=1)
+            sv.d2_x = x
+            y = Act(nq, d, pl, dev)
+            sv.d2_mean, sv.d2_rstd = torch.empty(nq, device=dev), torch.empty(nq, device=dev)
+            ops.ln_fwd(x, P("decoder.hierarchical_decoder.norm.weight"), P("decoder.hierarchical_decoder.norm.bias"), y,
+                       sv.d2_mean, sv.d2_rstd, nq, d)
+            sv.d2_y = y
+            vis_logits = torch.empty(nq, 2, device=dev)
+            w, _ = self._pack("decoder.hierarchical_fcn.visibility_fcn.weight")
+            ops.linear(y, w, nq, 2, d, bias=P("decoder.hierarchical_fcn.visibility_fcn.bias"), out_f32=vis_logits)
+            zp32, zp_act = torch.empty(nq, dz, device=dev), Act(nq, dz, pl, dev)
+            w, _ = self._pack("decoder.hierarchical_fcn.z_fcn.weight")
+            ops.linear(y, w, nq, dz, d, bias=P("decoder.hierarchical_fcn.z_fcn.bias"), out_f32=zp32, out_act=zp_act)
+            sv.zpath_act = zp_act
+            if inp["return_hierarch"]:
+                return [vis_logits, zp32], sv
+            zmem, nseq_d, lab_rpg = zp_act, nq, Gp
+        else:
+            vis_logits = None
+            zmem, nseq_d, lab_rpg = z_act, N, 1
+        Ld = (cfg.max_seq_len if two else cfg.max_total_len) + 1
+        Md = nseq_d * Ld
+        sv.nseq_d, sv.Ld, sv.Md = nseq_d, Ld, Md
+        x = torch.empty(Md, d, device=dev)
+        ops.rows_embed_fwd(None, P("decoder.embedding.PE.pos_embed.weight"), x, Md, Ld, d, self._drop(sv, "dec.pe", 0.1))
+        x = self._stack_fwd(sv, "decoder.decoder", cfg.n_layers_decode, x, Md, Ld, nseq_d, None, zmem=zmem, lab=lab_d,
+                            lab_rpg=lab_rpg)
+        sv.d1_x = x
+        y = Act(Md, d, pl, dev)
+        sv.d1_mean, sv.d1_rstd = torch.empty(Md, device=dev), torch.empty(Md, device=dev)
+        ops.ln_fwd(x, P("decoder.decoder.norm.weight"), P("decoder.decoder.norm.bias"), y, sv.d1_mean, sv.d1_rstd, Md, d)
+        sv.d1_y = y
+        nc, na_out = cfg.n_commands, cfg.n_args * self.args_dim
+        cmd_logits = torch.empty(Md, nc, device=dev)
+        w, _ = self._pack("decoder.fcn.command_fcn.weight")
+        ops.linear(y, w, Md, nc, d, bias=P("decoder.fcn.command_fcn.bias"), out_f32=cmd_logits)   # basic_blocks.py:18
+        args_logits = torch.empty(Md, na_out, device=dev)
+        w, _ = self._pack("decoder.fcn.args_fcn.weight")
+        ops.linear(y, w, Md, na_out, d, bias=P("decoder.fcn.args_fcn.bias"), out_f32=args_logits)  # basic_blocks.py:20
+        outs = [cmd_logits, args_logits]
+        if two:
+            outs.append(vis_logits)
+        if cfg.use_vae and sv.has_encoder:
+            outs += [sv.mu, sv.ls]
+        return outs, sv
+
+    # =================================================================================================
+    # backward
+    # =================================================================================================
+    def _layer_bwd(self, sv, gd, pre, dx2, dx2_act, M, L, nseq, key_valid, prev_drop, want_dact):
+        """dx2: fp32 grad of the layer output; dx2_act = dropout-masked act copy (operand of the FFN2 backward).
+        Returns (dx0, dx0_act or None, dx1) where dx1 is the grad at the post-attention residual (rowvec branch)."""
+        cfg = self.cfg
+        d, ff, H = cfg.d_model, cfg.dim_feedforward, cfg.n_heads
+        hd = d // H
+        s = sv.layers[pre]
+        dev, pl = dx2.device, self.planes
+        P = lambda n: self._param(pre + "." + n)
+        G = lambda n: gd[pre + "." + n]
+        pff = self._drop(sv, pre + ".dropff")
+        # ---- FFN ----
+        ops.colsum(dx2_act, M, d, G("linear2.bias"))
+        ops.outer(dx2_act, s["h"], M, d, ff, G("linear2.weight"))
+        dh = Act(M, ff, pl, dev)
+        _, w2t = self._pack(pre + ".linear2.weight")
+        ops.linear(dx2_act, w2t, M, ff, d, mask=s["h"], mask_scale=1.0 / (1.0 - pff[0]) if pff[0] > 0 else 1.0, out_act=dh)
+        ops.colsum(dh, M, ff, G("linear1.bias"))
+        ops.outer(dh, s["b"], M, ff, d, G("linear1.weight"))
+        db = Act(M, d, pl, dev)
+        _, w1t = self._pack(pre + ".linear1.weight")
+        ops.linear(dh, w1t, M, d, ff, out_act=db)
+        dx1 = torch.empty(M, d, device=dev)
+        dt = Act(M, d, pl, dev)
+        ops.ln_bwd(s["x1"], s["mean2"], s["rstd2"], P("norm2.weight"), M, d, dy=db, dx_in=dx2, dx_out=dx1, dact=dt,
+                   drop=self._drop(sv, pre + ".drop1"), dgamma=G("norm2.weight"), dbeta=G("norm2.bias"))
+        # ---- attention ----
+        ops.colsum(dt, M, d, G("self_attn.out_proj.bias"))
+        ops.outer(dt, s["o"], M, d, d, G("self_attn.out_proj.weight"))
+        do = Act(M, d, pl, dev)
+        _, wot = self._pack(pre + ".self_attn.out_proj.weight")
+        ops.linear(dt, wot, M, d, d, out_act=do)
+        dqkv = Act(M, 3 * d, pl, dev)
+        ops.attn_bwd(s["qkv"], key_valid, do, dqkv, nseq, L, H, hd, float(hd) ** -0.5, self._drop(sv, pre + ".attn"))
+        ops.colsum(dqkv, M, 3 * d, G("self_attn.in_proj_bias"))
+        ops.outer(dqkv, s["a"], M, 3 * d, d, G("self_attn.in_proj_weight"))
+        da = Act(M, d, pl, dev)
+        _, wit = self._pack(pre + ".self_attn.in_proj_weight")
+        ops.linear(dqkv, wit, M, d, 3 * d, out_act=da)
+        dx0 = torch.empty(M, d, device=dev)
+        dx0_act = Act(M, d, pl, dev) if want_dact else None
+        ops.ln_bwd(s["x"], s["mean1"], s["rstd1"], P("norm1.weight"), M, d, dy=da, dx_in=dx1, dx_out=dx0, dact=dx0_act,
+                   drop=prev_drop, dgamma=G("norm1.weight"), dbeta=G("norm1.bias"))
+        return dx0, dx0_act, dx1
+
+    def _globals_bwd(self, sv, gd, pre, dx1, n_groups, L, zmem, dzmem, lab, dlab, lab_rows_per_group, lab_rpg):
+        """Gradients of the rowvec branch of one layer (see _globals_fwd).  dzmem / dlab: fp32 accumulators or None."""
+        cfg = self.cfg
+        d = cfg.d_model
+        dev, pl = dx1.device, self.planes
+        if zmem is not None:
+            dgv = torch.empty(n_groups, d, device=dev)
+            ops.seg_sum(dx1, n_groups, L, d, out_f32=dgv)
+            dg = Act(n_groups, d, pl, dev)
+            ops.cast_act(dgv, n_groups, d, out=dg, drop=self._drop(sv, pre + ".dropg"))
+            ops.colsum(dg, n_groups, d, gd[pre + ".linear_global.bias"])
+            ops.outer(dg, zmem, n_groups, d, cfg.dim_z, gd[pre + ".linear_global.weight"])
+            _, wt = self._pack(pre + ".linear_global.weight")
+            ops.linear(dg, wt, n_groups, cfg.dim_z, d, residual=dzmem, out_f32=dzmem)
+            if lab is not None:
+                N = lab.rows
+                if lab_rpg > 1:
+                    d2v = torch.empty(N, d, device=dev)
+                    ops.seg_sum(dgv, N, lab_rpg, d, out_f32=d2v)
+                else:
+                    d2v = dgv
+        elif lab is not None:
+            N = lab.rows
+            d2v = torch.empty(N, d, device=dev)
+            ops.seg_sum(dx1, N, lab_rows_per_group, d, out_f32=d2v)
+        if lab is not None:
+            dg2 = Act(N, d, pl, dev)
+            ops.cast_act(d2v, N, d, out=dg2, drop=self._drop(sv, pre + ".dropg2"))
+            ops.colsum(dg2, N, d, gd[pre + ".linear_global2.bias"])
+            ops.outer(dg2, lab, N, d, cfg.dim_label, gd[pre + ".linear_global2.weight"])
+            _, wt = self._pack(pre + ".linear_global2.weight")
+            ops.linear(dg2, wt, N, cfg.dim_label, d, residual=dlab, out_f32=dlab)
+
+    def _stack_bwd(self, sv, gd, pre, n_layers, dx, dx_act, M, L, nseq, key_valid, zmem=None, dzmem=None, lab=None,
+                   dlab=None, lab_rows_per_group=1, lab_rpg=1):
+        """Reverse pass over a stack; dx / dx_act are the grads at the stack's last residual (after the final-norm bwd)."""
+        for i in reversed(range(n_layers)):
+            lp = "%s.layers.%d" % (pre, i)
+            prev = self._drop(sv, "%s.layers.%d.drop2" % (pre, i - 1)) if i > 0 else (0.0, 0, 0)
+            dx, dx_act, dx1 = self._layer_bwd(sv, gd, lp, dx, dx_act, M, L, nseq, key_valid, prev, want_dact=i > 0)
+            if zmem is not None or lab is not None:
+                self._globals_bwd(sv, gd, lp, dx1, nseq, L, zmem, dzmem, lab, dlab, lab_rows_per_group, lab_rpg)
+        return dx
+
+    def _head_bwd(self, gd, name, sources, y, M, n_out, d, dy32):
+        """Backward of one output Linear (weights `name`) for a list of (dl act, scale_dev) gradient sources; the input
+        gradient is accumulated into the fp32 buffer dy32 [M, d]."""
+        _, wt = self._pack(name + ".weight")
+        for dl, sc in sources:
+            ops.colsum(dl, M, n_out, gd[name + ".bias"], alpha_dev=sc)
+            ops.outer(dl, y, M, n_out, d, gd[name + ".weight"], alpha_dev=sc)
+            ops.linear(dl, wt, M, d, n_out, acc_scale=sc, residual=dy32, out_f32=dy32)
+
+    def _backward_impl(self, sv, out_grads, g_token):
+        cfg = self.cfg
+        d, dz = cfg.d_model, cfg.dim_z
+        two = cfg.encode_stages == 2
+        pl = self.planes
+        P = self._param
+        params = [P(n) for n in self._pnames]
+        dev = params[0].device
+        sizes = [p.numel() for p in params]
+        flat = torch.zeros(sum(sizes), device=dev)
+        gd, off = {}, 0
+        for n, p, sz in zip(self._pnames, params, sizes):
+            gd[n] = flat[off:off + sz].view(p.shape)
+            off += sz
+        handle = getattr(sv, "handle", None)
+        fused = g_token is not None and handle is not None and handle.dl_args is not None
+        N = sv.N
+
+        def explicit(g, rows, cols, ld):
+            a = Act(rows, cols, pl, dev, ld=ld, zero=True)
+            ops.cast_act(g.contiguous().view(rows, cols), rows, cols, out=a)
+            return a
+
+        it = iter(out_grads)
+        encode_only = not hasattr(sv, "d1_y")
+        dz32 = torch.zeros(N, dz, device=dev)          # gradient w.r.t. the latent z
+        dmu_ext = dls_ext = None
+        if encode_only:
+            g = next(it)
+            if g is not None:
+                dz32 += g.reshape(N, dz)
+        else:
+            g_cmd, g_args = next(it), next(it)
+            g_vis = next(it) if two else None
+            if cfg.use_vae and sv.has_encoder:
+                dmu_ext, dls_ext = next(it), next(it)
+            Md, Ld, nseq_d = sv.Md, sv.Ld, sv.nseq_d
+            nc, na_out = cfg.n_commands, cfg.n_args * self.args_dim
+            src_args, src_cmd, src_vis = [], [], []
+            if fused:
+                sc = handle.scales
+                src_args.append((handle.dl_args, sc[0:1]))
+                src_cmd.append((handle.dl_cmd, sc[1:2]))
+                if two:
+                    src_vis.append((handle.dl_vis, sc[2:3]))
+            if g_args is not None:
+                src_args.append((explicit(g_args, Md, na_out, _r8(na_out)), None))
+            if g_cmd is not None:
+                src_cmd.append((explicit(g_cmd, Md, nc, 8), None))
+            if g_vis is not None:
+                src_vis.append((explicit(g_vis, N * cfg.num_groups_proposal, 2, 8), None))
+            # ---- D1 heads + final norm ----
+            dy32 = torch.zeros(Md, d, device=dev)
+            self._head_bwd(gd, "decoder.fcn.args_fcn", src_args, sv.d1_y, Md, na_out, d, dy32)
+            self._head_bwd(gd, "decoder.fcn.command_fcn", src_cmd, sv.d1_y, Md, nc, d, dy32)
+            dy = Act(Md, d, pl, dev)
+            ops.cast_act(dy32, Md, d, out=dy)
+            nl = cfg.n_layers_decode
+            dx, dxa = torch.empty(Md, d, device=dev), Act(Md, d, pl, dev)
+            ops.ln_bwd(sv.d1_x, sv.d1_mean, sv.d1_rstd, P("decoder.decoder.norm.weight"), Md, d, dy=dy, dx_out=dx,
+                       dact=dxa, drop=self._drop(sv, "decoder.decoder.layers.%d.drop2" % (nl - 1)),
+                       dgamma=gd["decoder.decoder.norm.weight"], dbeta=gd["decoder.decoder.norm.bias"])
+            dlab_d = torch.zeros(N, cfg.dim_label, device=dev) if cfg.label_condition else None
+            if two:
+                Gp = cfg.num_groups_proposal
+                nq = N * Gp
+                dzp32 = torch.zeros(nq, dz, device=dev)
+                dx = self._stack_bwd(sv, gd, "decoder.decoder", nl, dx, dxa, Md, Ld, nseq_d, None, zmem=sv.zpath_act,
+                                     dzmem=dzp32, lab=sv.lab_d, dlab=dlab_d, lab_rpg=Gp)
+            else:
+                dx = self._stack_bwd(sv, gd, "decoder.decoder", nl, dx, dxa, Md, Ld, nseq_d, None, zmem=sv.z_act,
+                                     dzmem=dz32, lab=sv.lab_d, dlab=dlab_d, lab_rpg=1)
+            ops.rows_embed_bwd(dx, None, gd["decoder.embedding.PE.pos_embed.weight"], nseq_d, Ld, d,
+                               self._drop(sv, "dec.pe", 0.1))
+            if two:
+                # ---- D2 heads (basic_blocks.py:33-39) ----
+                dzp = Act(nq, dz, pl, dev)
+                ops.cast_act(dzp32, nq, dz, out=dzp)
+                dy32 = torch.zeros(nq, d, device=dev)
+                self._head_bwd(gd, "decoder.hierarchical_fcn.z_fcn", [(dzp, None)], sv.d2_y, nq, dz, d, dy32)
+                self._head_bwd(gd, "decoder.hierarchical_fcn.visibility_fcn", src_vis, sv.d2_y, nq, 2, d, dy32)
+                dy = Act(nq, d, pl, dev)
+                ops.cast_act(dy32, nq, d, out=dy)
+                dx, dxa = torch.empty(nq, d, device=dev), Act(nq, d, pl, dev)
+                ops.ln_bwd(sv.d2_x, sv.d2_mean, sv.d2_rstd, P("decoder.hierarchical_decoder.norm.weight"), nq, d, dy=dy,
+                           dx_out=dx, dact=dxa, drop=self._drop(sv, "decoder.hierarchical_decoder.layers.%d.drop2" % (nl - 1)),
+                           dgamma=gd["decoder.hierarchical_decoder.norm.weight"],
+                           dbeta=gd["decoder.hierarchical_decoder.norm.bias"])
+                dx = self._stack_bwd(sv, gd, "decoder.hierarchical_decoder", nl, dx, dxa, nq, Gp, N, None, zmem=sv.z_act,
+                                     dzmem=dz32, lab=sv.lab_d, dlab=dlab_d, lab_rpg=1)
+                ops.rows_embed_bwd(dx, None, gd["decoder.hierarchical_embedding.PE.pos_embed.weight"], N, Gp, d,
+                                   self._drop(sv, "dec.pe2", 0.1))
+            if cfg.label_condition:
+                ops.scatter_rows(dlab_d, sv.label, N, cfg.dim_label, gd["decoder.label_embedding.label_embedding.weight"])
+
+        if sv.has_encoder:
+            # ---- latent (model.py:361-367) ----
+            dzin = torch.zeros(N, d, device=dev)        # grad w.r.t. the ResNet output
+            if cfg.use_vae:
+                dmu, dls = torch.empty(N, dz, device=dev), torch.empty(N, dz, device=dev)
+                kl_coef = handle.scales[3:4] if fused else None
+                ops.vae_bwd(sv.mu, sv.ls, sv.eps, dz32, kl_coef, handle.loss_out if fused else None,
+                            1.0 / (N * dz * getattr(handle, "world", 1)) if fused else 0.0, dmu, dls, N * dz)
+                if dmu_ext is not None:
+                    dmu += dmu_ext.reshape(N, dz)
+                if dls_ext is not None:
+                    dls += dls_ext.reshape(N, dz)
+                for nm, g32 in (("vae.enc_mu_fcn", dmu), ("vae.enc_sigma_fcn", dls)):
+                    ga = Act(N, dz, pl, dev)
+                    ops.cast_act(g32, N, dz, out=ga)
+                    self._head_bwd(gd, nm, [(ga, None)], sv.lat_in, N, dz, d, dzin)
+            else:
+                ga = Act(N, dz, pl, dev)
+                ops.cast_act(dz32, N, dz, out=ga)
+                self._head_bwd(gd, "bottleneck.bottleneck", [(ga, None)], sv.lat_in, N, dz, d, dzin)
+            if cfg.use_resnet:
+                for i in range(4, 0, -1):
+                    za, ra = sv.res[i - 1]
+                    dr = Act(N, d, pl, dev)
+                    ops.cast_act(dzin, N, d, out=dr, mask=ra, mask_scale=1.0)
+                    self._head_bwd(gd, "resnet.linear%d.0" % i, [(dr, None)], za, N, d, d, dzin)
+            # ---- encoder ----
+            G, L = sv.G, sv.L
+            nseq, M1 = N * G, N * G * L
+            nl = cfg.n_layers
+            dlab_e = torch.zeros(N, cfg.dim_label, device=dev) if cfg.label_condition else None
+            if two:
+                dx, dxa = torch.empty(nseq, d, device=dev), Act(nseq, d, pl, dev)
+                ops.ln_bwd(sv.e2_x, sv.e2_mean, sv.e2_rstd, P("encoder.hierarchical_encoder.norm.weight"), nseq, d,
+                           dz=dzin, valid=sv.visible, inv_cnt=sv.e2_icnt, L=G, dx_out=dx, dact=dxa,
+                           drop=self._drop(sv, "encoder.hierarchical_encoder.layers.%d.drop2" % (nl - 1)),
+                           dgamma=gd["encoder.hierarchical_encoder.norm.weight"],
+                           dbeta=gd["encoder.hierarchical_encoder.norm.bias"])
+                dx = self._stack_bwd(sv, gd, "encoder.hierarchical_encoder", nl, dx, dxa, nseq, G, N, sv.visible,
+                                     lab=sv.lab_e, dlab=dlab_e, lab_rows_per_group=G)
+                dzp = torch.empty(nseq, d, device=dev)
+                ops.rows_embed_bwd(dx, dzp, gd["encoder.hierarchical_PE.pos_embed.weight"], N, G, d,
+                                   self._drop(sv, "enc.pe2", 0.1))
+            else:
+                dzp = dzin
+            dx, dxa = torch.empty(M1, d, device=dev), Act(M1, d, pl, dev)
+            ops.ln_bwd(sv.e1_x, sv.e1_mean, sv.e1_rstd, P("encoder.encoder.norm.weight"), M1, d, dz=dzp,
+                       valid=sv.key_valid, inv_cnt=sv.e1_icnt, L=L, dx_out=dx, dact=dxa,
+                       drop=self._drop(sv, "encoder.encoder.layers.%d.drop2" % (nl - 1)),
+                       dgamma=gd["encoder.encoder.norm.weight"], dbeta=gd["encoder.encoder.norm.bias"])
+            dx = self._stack_bwd(sv, gd, "encoder.encoder", nl, dx, dxa, M1, L, nseq, sv.key_valid, lab=sv.lab_e,
+                                 dlab=dlab_e, lab_rows_per_group=G * L)
+            V, na = cfg.args_dim + 1, cfg.n_args
+            scratch = torch.empty(na * V, d, device=dev)
+            ops.embed_bwd(sv.commands, sv.args, sv.grp, dx, P("encoder.embedding.arg_embed.weight"),
+                          P("encoder.embedding.embed_fcn.weight"), gd["encoder.embedding.command_embed.weight"],
+                          gd["encoder.embedding.pos_encoding.pos_embed.weight"],
+                          None if two else gd["encoder.embedding.group_embed.weight"],
+                          gd["encoder.embedding.arg_embed.weight"], gd["encoder.embedding.embed_fcn.weight"],
+                          gd["encoder.embedding.embed_fcn.bias"], scratch, nseq, L, V, na, d, cfg.max_num_groups + 2,
+                          self._drop(sv, "enc.pe", 0.1))
+            if cfg.label_condition:
+                ops.scatter_rows(dlab_e, sv.label, N, cfg.dim_label, gd["encoder.label_embedding.label_embedding.weight"])
+
+        if self.process_group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.process_group)   # the ONE data-path collective
+        sv.layers.clear()
+        return [gd[n] for n in self._pnames]

@@ -1,0 +1,367 @@
+"""Per-kernel parity on the GPU: every C-ABI entry point against a plain fp32 PyTorch restatement of the same op
+(teacher-forced: identical inputs, so only accumulation order / operand rounding differ)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _ops():
+    from deepsvg_b200 import ops
+    return ops
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+def _rel(a, b):
+    return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
+
+
+# ------------------------------------------------------------------------------------------------ GEMMs
+@pytest.mark.parametrize("planes", [1, 2])
+@pytest.mark.parametrize("M,N,K", [(512, 256, 256), (300, 768, 256), (496, 7, 256), (992, 2827, 256), (1024, 256, 512),
+                                   (64, 256, 64)])
+def test_linear_matches_fp32(planes, M, N, K):
+    ops = _ops()
+    X, W, b = _rand(M, K, seed=1), _rand(N, K, seed=2, scale=K ** -0.5), _rand(N, seed=3)
+    xa, wa = ops.act_from_float(X, planes), ops.act_from_float(W, planes)
+    out = torch.empty(M, N, device=DEV)
+    ops.linear(xa, wa, M, N, K, bias=b, out_f32=out)
+    ref = (xa.float().double() @ wa.float().double().t()).float() + b
+    assert _rel(out, ref) < 2e-5
+    if planes == 2:  # bf16x3 must track the un-rounded fp32 product
+        full = (X.double() @ W.double().t()).float() + b
+        assert _rel(out, full) < 3e-5
+
+
+def test_linear_full_epilogue():
+    ops = _ops()
+    M, N, K, rpg = 620, 512, 256, 31
+    X, W, b = _rand(M, K, seed=1), _rand(N, K, seed=2, scale=K ** -0.5), _rand(N, seed=3)
+    res, rv = _rand(M, N, seed=4), _rand(M // rpg, N, seed=5)
+    msk = (_rand(M, N, seed=6) > 0).float()
+    sc = torch.tensor([0.75], device=DEV)
+    xa, wa, ma = ops.act_from_float(X, 1), ops.act_from_float(W, 1), ops.act_from_float(msk, 1)
+    out = torch.empty(M, N, device=DEV)
+    oa = ops.Act(M, N, 2, DEV)
+    ops.linear(xa, wa, M, N, K, bias=b, scale_cols=100, scale=0.5, relu=True, rowvec=rv, rows_per_group=rpg, mask=ma,
+               mask_scale=1.25, residual=res, out_f32=out, out_act=oa, acc_scale=sc)
+    ref = (xa.float() @ wa.float().t()) * 0.75 + b
+    ref[:, :100] *= 0.5
+    ref = torch.relu(ref) + rv.repeat_interleave(rpg, 0)
+    ref = ref * msk * 1.25 + res
+    assert _rel(out, ref) < 2e-5
+    assert _rel(oa.float(), ref) < 2e-4
+
+
+def test_linear_dropout_statistics_and_determinism():
+    ops = _ops()
+    M, N, K = 1024, 256, 64
+    X = torch.ones(M, K, device=DEV)
+    W = torch.ones(N, K, device=DEV) / K
+    xa, wa = ops.act_from_float(X, 1), ops.act_from_float(W, 1)
+    o1, o2, o3 = (torch.empty(M, N, device=DEV) for _ in range(3))
+    ops.linear(xa, wa, M, N, K, drop=(0.1, 7, 1234), out_f32=o1)
+    ops.linear(xa, wa, M, N, K, drop=(0.1, 7, 1234), out_f32=o2)
+    ops.linear(xa, wa, M, N, K, drop=(0.1, 8, 1234), out_f32=o3)
+    assert torch.equal(o1, o2) and not torch.equal(o1, o3)
+    keep = (o1 != 0).float().mean().item()
+    assert abs(keep - 0.9) < 0.005
+    assert torch.allclose(o1[o1 != 0], torch.tensor(1 / 0.9, device=DEV), rtol=1e-5)
+    # cast_act regenerates the same mask from (seed, site, row*N+col)
+    ca = ops.Act(M, N, 1, DEV)
+    ops.cast_act(torch.ones(M, N, device=DEV), M, N, out=ca, drop=(0.1, 7, 1234))
+    assert torch.equal(ca.float() != 0, o1 != 0)
+
+
+@pytest.mark.parametrize("planes", [1, 2])
+@pytest.mark.parametrize("M,P,Q", [(4096, 768, 256), (1000, 300, 200), (2048, 2827, 64), (992, 7, 256), (130, 256, 512)])
+def test_outer_matches_fp32(planes, M, P, Q):
+    ops = _ops()
+    A, B = _rand(M, P, seed=1), _rand(M, Q, seed=2)
+    lda, ldb = (P + 7) // 8 * 8, (Q + 7) // 8 * 8
+    aa, ba = ops.act_from_float(A, planes, ld=lda), ops.act_from_float(B, planes, ld=ldb)
+    Cout = torch.ones(P, Q, device=DEV)
+    sc = torch.tensor([2.0], device=DEV)
+    ops.outer(aa, ba, M, P, Q, Cout, alpha=0.5, alpha_dev=sc)
+    ref = (aa.float().double().t() @ ba.float().double()).float() + 1.0
+    assert _rel(Cout, ref) < 2e-5
+    if planes == 2:
+        assert _rel(Cout, (A.double().t() @ B.double()).float() + 1.0) < 3e-5
+
+
+# ------------------------------------------------------------------------------------------------ LayerNorm
+@pytest.mark.parametrize("D", [128, 256, 512])
+def test_layernorm_fwd_bwd(D):
+    ops = _ops()
+    M = 777
+    x, g, b = _rand(M, D, seed=1), 1 + 0.1 * _rand(D, seed=2), 0.1 * _rand(D, seed=3)
+    y = ops.Act(M, D, 2, DEV)
+    mean, rstd = torch.empty(M, device=DEV), torch.empty(M, device=DEV)
+    ops.ln_fwd(x, g, b, y, mean, rstd, M, D)
+    xr = x.clone().requires_grad_(True)
+    gr, br = g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = F.layer_norm(xr, (D,), gr, br, 1e-5)
+    assert _rel(y.float(), ref.detach()) < 1e-4
+    dy, dx_in = _rand(M, D, seed=4), _rand(M, D, seed=5)
+    dya = ops.act_from_float(dy, 2)
+    ref.backward(dya.float())
+    dx = torch.empty(M, D, device=DEV)
+    dact = ops.Act(M, D, 2, DEV)
+    dg, db = torch.zeros(D, device=DEV), torch.zeros(D, device=DEV)
+    ops.ln_bwd(x, mean, rstd, g, M, D, dy=dya, dx_in=dx_in, dx_out=dx, dact=dact, dgamma=dg, dbeta=db)
+    assert _rel(dx, xr.grad + dx_in) < 2e-5
+    assert _rel(dact.float(), xr.grad + dx_in) < 1e-4
+    assert _rel(dg, gr.grad) < 2e-5 and _rel(db, br.grad) < 2e-5
+
+
+def test_layernorm_pool_fwd_bwd():
+    ops = _ops()
+    nseq, L, D = 96, 31, 256
+    M = nseq * L
+    x, g, b = _rand(M, D, seed=1), 1 + 0.1 * _rand(D, seed=2), 0.1 * _rand(D, seed=3)
+    lens = torch.randint(1, L + 1, (nseq,), generator=torch.Generator().manual_seed(9))
+    valid = (torch.arange(L)[None, :] < lens[:, None]).to(torch.uint8).to(DEV).reshape(-1).contiguous()
+    z = torch.empty(nseq, D, device=DEV)
+    mean, rstd, ic = torch.empty(M, device=DEV), torch.empty(M, device=DEV), torch.empty(nseq, device=DEV)
+    ops.ln_pool_fwd(x, g, b, valid, z, mean, rstd, ic, nseq, L, D)
+    xr = x.clone().requires_grad_(True)
+    gr, br = g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    w = valid.float().reshape(nseq, L, 1)
+    ref = (F.layer_norm(xr, (D,), gr, br, 1e-5).reshape(nseq, L, D) * w).sum(1) / w.sum(1)
+    assert _rel(z, ref.detach()) < 2e-5
+    dz = _rand(nseq, D, seed=4)
+    ref.backward(dz)
+    dx = torch.empty(M, D, device=DEV)
+    dg, db = torch.zeros(D, device=DEV), torch.zeros(D, device=DEV)
+    ops.ln_bwd(x, mean, rstd, g, M, D, dz=dz, valid=valid, inv_cnt=ic, L=L, dx_out=dx, dgamma=dg, dbeta=db)
+    assert _rel(dx, xr.grad) < 2e-5
+    assert _rel(dg, gr.grad) < 2e-5 and _rel(db, br.grad) < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------ attention
+@pytest.mark.parametrize("L,H,hd,masked", [(32, 8, 32, True), (31, 8, 32, False), (8, 8, 32, True), (52, 4, 64, True),
+                                           (66, 8, 64, False), (8, 4, 16, False)])
+def test_attention_fwd_bwd(L, H, hd, masked):
+    ops = _ops()
+    nseq, d = 37, H * hd
+    M = nseq * L
+    qkv = _rand(M, 3 * d, seed=1, scale=0.7)
+    qa = ops.act_from_float(qkv, 2)
+    qv = qa.float().clone().requires_grad_(True)
+    valid = None
+    vmask = None
+    if masked:
+        lens = torch.randint(1, L + 1, (nseq,), generator=torch.Generator().manual_seed(3))
+        vmask = (torch.arange(L)[None, :] < lens[:, None]).to(DEV)
+        valid = vmask.to(torch.uint8).reshape(-1).contiguous()
+    out = ops.Act(M, d, 2, DEV)
+    ops.attn_fwd(qa, valid, out, nseq, L, H, hd, (0.0, 0, 0))
+    q, k, v = (t.reshape(nseq, L, H, hd).transpose(1, 2) for t in qv.split(d, dim=-1))
+    s = q @ k.transpose(-1, -2)
+    if masked:
+        s = s.masked_fill(~vmask[:, None, None, :], float("-inf"))
+    ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(M, d)
+    assert _rel(out.float(), ref.detach()) < 1e-4
+    do = _rand(M, d, seed=5)
+    da = ops.act_from_float(do, 2)
+    ref.backward(da.float())
+    dqkv = ops.Act(M, 3 * d, 2, DEV)
+    ops.attn_bwd(qa, valid, da, dqkv, nseq, L, H, hd, 1.0, (0.0, 0, 0))
+    assert _rel(dqkv.float(), qv.grad) < 1e-4
+
+
+def test_attention_dropout_consistent_fwd_bwd():
+    """With dropout the backward must use the forward's mask: check d(out . w)/dv against finite structure."""
+    ops = _ops()
+    nseq, L, H, hd = 5, 32, 8, 32
+    d, M = H * hd, nseq * L
+    qkv = _rand(M, 3 * d, seed=1, scale=0.5)
+    qa = ops.act_from_float(qkv, 2)
+    drop = (0.3, 11, 99)
+    o1, o2 = ops.Act(M, d, 2, DEV), ops.Act(M, d, 2, DEV)
+    ops.attn_fwd(qa, None, o1, nseq, L, H, hd, drop)
+    ops.attn_fwd(qa, None, o2, nseq, L, H, hd, drop)
+    assert torch.equal(o1.t, o2.t)
+    # out is linear in v for fixed probabilities+mask: out(v) . g == v . dv(g)
+    g = _rand(M, d, seed=2)
+    ga = ops.act_from_float(g, 2)
+    dqkv = ops.Act(M, 3 * d, 2, DEV)
+    ops.attn_bwd(qa, None, ga, dqkv, nseq, L, H, hd, 1.0, drop)
+    lhs = (o1.float() * ga.float()).sum().item()
+    rhs = (qa.float()[:, 2 * d:] * dqkv.float()[:, 2 * d:]).sum().item()
+    assert abs(lhs - rhs) < 2e-3 * abs(lhs)
+
+
+# ------------------------------------------------------------------------------------------------ embedding
+@pytest.mark.parametrize("use_grp", [False, True])
+def test_embedding_fwd_bwd(use_grp):
+    ops = _ops()
+    from oracle import svg_oracle as O
+    cfg = O.make_cfg("one_stage" if use_grp else "hierarchical", max_total_len=30)
+    n = 6
+    cmd, arg = O.synth_batch(cfg, n, seed=5)
+    G, L = cmd.shape[1], cmd.shape[2]
+    nseq, T, d, V, na = n * G, n * G * L, 256, 257, 11
+    cmd, arg = cmd.to(DEV).contiguous(), arg.to(DEV).contiguous()
+    Ec, Ea = _rand(7, d, seed=1), _rand(V, 64, seed=2)
+    W, b = _rand(d, 64 * na, seed=3, scale=0.05), _rand(d, seed=4)
+    Pt, Gt = _rand(L, d, seed=5), _rand(10, d, seed=6)
+    grp = torch.empty(T, dtype=torch.uint8, device=DEV)
+    ops.seq_prep(cmd, nseq, L, None, None, None, grp, None)
+    table, base = torch.empty(na * V, d, device=DEV), torch.empty(d, device=DEV)
+    ops.embed_fold(Ea, W, b, table, base, V, na, d)
+    x = torch.empty(T, d, device=DEV)
+    ops.embed_fwd(cmd, arg, grp if use_grp else None, Ec, table, base, Pt, Gt if use_grp else None, x, T, L, V, na, d,
+                  (0.0, 0, 0))
+    leaves = [t.clone().requires_grad_(True) for t in (Ec, Ea, W, b, Pt, Gt)]
+    ec, ea, w, bb, pt, gt = leaves
+    ci = cmd.long().reshape(-1)
+    ref = ec[ci] + F.linear(ea[(arg + 1).long()].reshape(T, -1), w, bb) + pt.repeat(nseq, 1)
+    if use_grp:
+        ref = ref + gt[(cmd.long() == 0).cumsum(-1).reshape(-1)]
+    assert _rel(x, ref.detach()) < 2e-5
+    dx = _rand(T, d, seed=7)
+    ref.backward(dx)
+    grads = [torch.zeros_like(t) for t in (Ec, Ea, W, b, Pt, Gt)]
+    scratch = torch.empty(na * V, d, device=DEV)
+    ops.embed_bwd(cmd, arg, grp if use_grp else None, dx, Ea, W, grads[0], grads[4], grads[5] if use_grp else None,
+                  grads[1], grads[2], grads[3], scratch, nseq, L, V, na, d, 10, (0.0, 0, 0))
+    for name, got, leaf in zip("Ec Ea W b Pt Gt".split(), grads, leaves):
+        if name == "Gt" and not use_grp:
+            continue
+        assert _rel(got, leaf.grad) < 5e-5, name
+
+
+def test_seq_prep_matches_oracle_masks():
+    ops = _ops()
+    from oracle import svg_oracle as O
+    cfg = O.make_cfg("hierarchical")
+    cmd, _ = O.synth_batch(cfg, 16, seed=3)
+    n, G, L = cmd.shape
+    c = cmd.to(DEV).contiguous()
+    nseq = n * G
+    fe = torch.empty(nseq, dtype=torch.int32, device=DEV)
+    vis = torch.empty(nseq, dtype=torch.uint8, device=DEV)
+    kv = torch.empty(nseq * L, dtype=torch.uint8, device=DEV)
+    grp = torch.empty(nseq * L, dtype=torch.uint8, device=DEV)
+    counts = torch.zeros(2, device=DEV)
+    ops.seq_prep(c, nseq, L, fe, vis, kv, grp, counts)
+    ci = cmd.long()
+    assert torch.equal(kv.cpu().bool().reshape(n, G, L), ~O.key_padding(ci))
+    assert torch.equal(vis.cpu().bool().reshape(n, G), O.visibility(ci))
+    assert torch.equal(grp.cpu().long().reshape(n, G, L), O.group_index(ci))
+    wc = (O.extended_padding(ci) * O.visibility(ci).unsqueeze(-1).float())[..., 1:]
+    wa = O.CMD_ARGS_MASK[ci[..., 1:]]
+    assert counts[0].item() == wc.sum().item() and counts[1].item() == wa.sum().item()
+
+
+def test_rows_embed_and_segsum():
+    ops = _ops()
+    nseq, L, d = 40, 31, 256
+    R = nseq * L
+    tab, add = _rand(L, d, seed=1), _rand(R, d, seed=2)
+    x = torch.empty(R, d, device=DEV)
+    ops.rows_embed_fwd(add, tab, x, R, L, d, (0.0, 0, 0))
+    assert torch.allclose(x, add + tab.repeat(nseq, 1))
+    dx = _rand(R, d, seed=3)
+    dadd, dtab = torch.empty(R, d, device=DEV), torch.zeros(L, d, device=DEV)
+    ops.rows_embed_bwd(dx, dadd, dtab, nseq, L, d, (0.0, 0, 0))
+    assert torch.equal(dadd, dx) and _rel(dtab, dx.reshape(nseq, L, d).sum(0)) < 1e-5
+    s = torch.empty(nseq, d, device=DEV)
+    ops.seg_sum(dx, nseq, L, d, out_f32=s)
+    assert _rel(s, dx.reshape(nseq, L, d).sum(1)) < 1e-5
+    cs = torch.zeros(d, device=DEV)
+    a = ops.act_from_float(dx, 2)
+    ops.colsum(a, R, d, cs)
+    assert _rel(cs, a.float().sum(0)) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ loss
+def test_cross_entropy_kernels():
+    ops = _ops()
+    from oracle import svg_oracle as O
+    cfg = O.make_cfg("hierarchical")
+    n = 8
+    cmd, arg = O.synth_batch(cfg, n, seed=11)
+    G, L = cmd.shape[1], cmd.shape[2]
+    nseq, Ld = n * G, L - 1
+    Md = nseq * Ld
+    al = _rand(Md, 11 * 257, seed=1, scale=2.0)
+    cl, vl = _rand(Md, 7, seed=2, scale=2.0), _rand(nseq, 2, seed=3)
+    c, a = cmd.to(DEV).contiguous(), arg.to(DEV).contiguous()
+    fe = torch.empty(nseq, dtype=torch.int32, device=DEV)
+    vis = torch.empty(nseq, dtype=torch.uint8, device=DEV)
+    counts, acc, out = torch.zeros(2, device=DEV), torch.zeros(8, device=DEV), torch.zeros(8, device=DEV)
+    ops.seq_prep(c, nseq, L, fe, vis, None, None, counts)
+    dla, dlc, dlv = ops.Act(Md, 2827, 2, DEV, ld=2880, zero=True), ops.Act(Md, 7, 2, DEV, ld=8), ops.Act(nseq, 2, 2, DEV, ld=8)
+    ops.ce_args(al, 2827, c, a, counts, dla, acc, nseq, L, 11, 257)
+    ops.ce_cmd(cl, c, fe, vis, counts, dlc, acc, nseq, L, 7)
+    ops.ce_vis(vl, vis, dlv, acc, nseq, 1.0 / nseq)
+    ops.loss_finalize(acc, counts, out, 1.0, 2.0, 1.0, 0.0, 0.1, 1.0 / nseq, 0.0, True, False)
+    leaves = [t.clone().requires_grad_(True) for t in (al, cl, vl)]
+    cfg.use_vae = False
+    o = {"command_logits": leaves[1].reshape(n, G, Ld, 7), "args_logits": leaves[0].reshape(n, G, Ld, 11, 257),
+         "visibility_logits": leaves[2].reshape(n, G, 1, 2), "tgt_commands": c, "tgt_args": a}
+    O.CMD_ARGS_MASK = O.CMD_ARGS_MASK.to(DEV)
+    try:
+        ls = O.loss(o, cfg)
+        for key, ten, leaf, dl in (("loss_args", al, leaves[0], dla), ("loss_cmd", cl, leaves[1], dlc),
+                                   ("loss_visibility", vl, leaves[2], dlv)):
+            g, = torch.autograd.grad(ls[key], leaf, retain_graph=True)
+            assert _rel(dl.float(), g) < 1e-4, key
+    finally:
+        O.CMD_ARGS_MASK = O.CMD_ARGS_MASK.cpu()
+    assert abs(out[0].item() - ls["loss"].item()) < 1e-5 * ls["loss"].item()
+    assert abs(out[1].item() - ls["loss_cmd"].item()) < 1e-5 and abs(out[2].item() - ls["loss_args"].item()) < 1e-5
+    assert abs(out[3].item() - ls["loss_visibility"].item()) < 1e-5
+    assert dla.t[:, :, 2827:].abs().max().item() == 0  # K padding of the head dgrad operand stays zero
+
+
+def test_vae_and_kl():
+    ops = _ops()
+    n, dz = 64, 256
+    mu, ls, eps, dz_ = _rand(n, dz, seed=1), _rand(n, dz, seed=2, scale=0.3), _rand(n, dz, seed=3), _rand(n, dz, seed=4)
+    z = torch.empty(n, dz, device=DEV)
+    ops.vae_fwd(mu, ls, eps, z, n * dz)
+    m, l = mu.clone().requires_grad_(True), ls.clone().requires_grad_(True)
+    zr = m + torch.exp(l / 2) * eps
+    assert _rel(z, zr.detach()) < 1e-6
+    kl = (-0.5 * torch.mean(1 + l - m.pow(2) - torch.exp(l))).clamp(min=0.1)
+    ((zr * dz_).sum() + 3.0 * kl).backward()
+    acc, out = torch.zeros(8, device=DEV), torch.zeros(8, device=DEV)
+    ops.kl_sum(mu, ls, acc, n * dz)
+    counts = torch.ones(2, device=DEV)
+    ops.loss_finalize(acc, counts, out, 0.0, 0.0, 0.0, 1.0, 0.1, 0.0, 1.0 / (n * dz), False, True)
+    assert abs(out[4].item() - kl.item()) < 1e-5
+    dmu, dls = torch.empty(n, dz, device=DEV), torch.empty(n, dz, device=DEV)
+    coef = torch.tensor([3.0], device=DEV)
+    ops.vae_bwd(mu, ls, eps, dz_, coef, out, 1.0 / (n * dz), dmu, dls, n * dz)
+    assert _rel(dmu, m.grad) < 1e-5 and _rel(dls, l.grad) < 1e-5
+
+
+def test_cast_transpose_and_labels():
+    ops = _ops()
+    R, Cc = 258, 300
+    x = _rand(R, Cc, seed=1)
+    a, at = ops.Act(R, Cc, 2, DEV, ld=304), ops.Act(Cc, R, 2, DEV, ld=264)
+    ops.cast_act(x, R, Cc, out=a, outT=at)
+    assert _rel(a.float(), x) < 1e-5 and _rel(at.float(), x.t()) < 1e-5
+    assert a.t[:, :, Cc:].abs().max().item() == 0 and at.t[:, :, R:].abs().max().item() == 0
+    table = _rand(52, 64, seed=2)
+    idx = torch.randint(0, 52, (40,), generator=torch.Generator().manual_seed(1)).to(DEV)
+    g = ops.Act(40, 64, 2, DEV)
+    ops.gather_rows(table, idx, 40, 64, g)
+    assert _rel(g.float(), table[idx]) < 1e-5
+    dt = torch.zeros(52, 64, device=DEV)
+    gr = _rand(40, 64, seed=3)
+    ops.scatter_rows(gr, idx, 40, 64, dt)
+    assert _rel(dt, torch.zeros(52, 64, device=DEV).index_add_(0, idx, gr)) < 1e-5
