@@ -9,6 +9,8 @@
 // warp-broadcast float4s; the L x L probability tile never leaves shared memory.  Attention is 2.4 % of the step's
 // FLOPs; this kernel is precision-exact for both fast and parity modes.
 #include "../../include/dsvg_b200.h"
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace dsvg {
@@ -246,6 +248,16 @@ static int launch_attn(bool bwd, const AttnArgs& a, cudaStream_t st) {
 }  // namespace dsvg
 using namespace dsvg;
 
+// tensor-core (mma.sync) fast path, attention_mma.cu
+int dsvg_attn_mma_fwd(const bf16* qkv, const uint8_t* valid, bf16* out, int nseq, int L, int H, Dropout drop,
+                      cudaStream_t st);
+int dsvg_attn_mma_bwd(const bf16* qkv, const uint8_t* valid, const bf16* dout, bf16* dqkv, int nseq, int L, int H,
+                      float q_scale, Dropout drop, cudaStream_t st);
+static bool use_mma(bool single_plane, int L, int head_dim) {
+  static const bool off = [] { const char* e = getenv("DSVG_ATTN"); return e && e[0] == 's'; }();  // "simt"
+  return !off && single_plane && head_dim == 32 && L <= 32;
+}
+
 extern "C" int dsvg_attn_fwd(const dsvg_bf16* qkv, size_t qkv_lo_off, const uint8_t* key_valid, dsvg_bf16* out,
                              size_t out_lo_off, int nseq, int L, int H, int head_dim, float drop_p, uint32_t drop_site,
                              uint64_t seed, void* stream) {
@@ -256,6 +268,8 @@ extern "C" int dsvg_attn_fwd(const dsvg_bf16* qkv, size_t qkv_lo_off, const uint
   a.nseq = nseq; a.L = L; a.H = H; a.scale = 1.f;
   a.drop = make_dropout(drop_p, drop_site, seed);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (use_mma(qkv_lo_off == 0 && out_lo_off == 0, L, head_dim))
+    return dsvg_attn_mma_fwd(a.qkv, key_valid, a.out, nseq, L, H, a.drop, st);
   if (head_dim == 32) return launch_attn<32>(false, a, st);
   if (head_dim == 64) return launch_attn<64>(false, a, st);
   if (head_dim == 16) return launch_attn<16>(false, a, st);
@@ -274,6 +288,8 @@ extern "C" int dsvg_attn_bwd(const dsvg_bf16* qkv, size_t qkv_lo_off, const uint
   a.nseq = nseq; a.L = L; a.H = H; a.scale = q_scale;
   a.drop = make_dropout(drop_p, drop_site, seed);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (use_mma(qkv_lo_off == 0 && dout_lo_off == 0 && dqkv_lo_off == 0, L, head_dim))
+    return dsvg_attn_mma_bwd(a.qkv, key_valid, a.dout, a.dqkv, nseq, L, H, q_scale, a.drop, st);
   if (head_dim == 32) return launch_attn<32>(true, a, st);
   if (head_dim == 64) return launch_attn<64>(true, a, st);
   if (head_dim == 16) return launch_attn<16>(true, a, st);

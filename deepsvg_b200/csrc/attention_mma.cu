@@ -1,0 +1,406 @@
+// Fast-mode attention for DeepSVG's tiny sequences on the warp-level tensor-core path (mma.sync m16n8k16, bf16 in,
+// fp32 accumulate): one warp owns one (sequence, head) pair, head_dim = 32, L <= 32 keys/queries padded to a
+// 32 x 32 tile.  Q, K, V (and dO in the backward) are staged in shared memory with coalesced 16-byte loads and
+// read back with ldmatrix; scores, probabilities and all gradients of the pair stay in registers / shared memory.
+//
+//   reference: functional.py:168-248 (see attention.cu for the fp32 SIMT version used in parity mode and for
+//   shapes this kernel does not cover).  tcgen05 is not used here on purpose: a 32 x 32 x 32 problem fills 1/16 of
+//   the smallest UMMA tile (hard part 2); attention is 2.4 % of the step's FLOPs.
+//
+// Dropout on the probabilities uses its own element numbering (8 consecutive Philox words per (row, lane-in-quad)),
+// identical in forward and backward of THIS kernel.
+#include "../../include/dsvg_b200.h"
+#include "common.cuh"
+
+namespace dsvg {
+extern unsigned long long g_launches;
+
+constexpr int kRow = 40;                   // smem row stride in bf16 (80 B: 16-byte aligned, conflict-free ldmatrix)
+constexpr int kTile = 32 * kRow;           // one 32 x 32 tile
+
+struct MmaAttnArgs {
+  const bf16* qkv;      // [nseq*L, 3d]
+  const uint8_t* valid; // [nseq*L] or null
+  bf16* out;            // fwd  [nseq*L, d]
+  const bf16* dout;     // bwd  [nseq*L, d]
+  bf16* dqkv;           // bwd  [nseq*L, 3d]
+  int nseq, L, H;
+  float scale;
+  Dropout drop;
+};
+
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+// ---- fragment loaders (tile = 32 x 32 bf16, row stride kRow) -------------------------------------------
+// A operand, rows [16*mt, +16), k columns [16*ks, +16): a0..a3 from one ldmatrix.x4
+__device__ __forceinline__ void load_a(uint32_t (&a)[4], uint32_t tile, int mt, int ks, int lane) {
+  const int m = lane >> 3, r = lane & 7;
+  ldsm_x4(a, tile + ((16 * mt + (m & 1) * 8 + r) * kRow + 16 * ks + (m >> 1) * 8) * 2);
+}
+// A operand taken TRANSPOSED from a row-major tile Z[k][m]: A[m][k] = Z[k][m]
+__device__ __forceinline__ void load_a_t(uint32_t (&a)[4], uint32_t tile, int mt, int ks, int lane) {
+  const int m = lane >> 3, r = lane & 7;
+  // matrices: (k0, m0) (k0, m0+8) (k0+8, m0) (k0+8, m0+8) -> a0 a1 a2 a3
+  ldsm_x4_t(a, tile + ((16 * ks + (m >> 1) * 8 + r) * kRow + 16 * mt + (m & 1) * 8) * 2);
+}
+// B operand ("col") for two adjacent n-tiles from row-major X[n][k] (K for Q.K^T, V for dO.V^T):
+// r0,r1 = b0,b1 of n-tile 2*np ; r2,r3 = b0,b1 of n-tile 2*np+1
+__device__ __forceinline__ void load_b_nk(uint32_t (&b)[4], uint32_t tile, int np, int ks, int lane) {
+  const int m = lane >> 3, r = lane & 7;
+  ldsm_x4(b, tile + ((16 * np + (m >> 1) * 8 + r) * kRow + 16 * ks + (m & 1) * 8) * 2);
+}
+// B operand for two adjacent n-tiles from row-major Y[k][n] (V for P.V, K for dS.K, Q / dO for the transposed products)
+__device__ __forceinline__ void load_b_kn(uint32_t (&b)[4], uint32_t tile, int np, int ks, int lane) {
+  const int m = lane >> 3, r = lane & 7;
+  ldsm_x4_t(b, tile + ((16 * ks + (m & 1) * 8 + r) * kRow + 16 * np + (m >> 1) * 8) * 2);
+}
+
+// stage a [L x 32] head slice (row stride ld elements) into a zero-padded 32 x 32 tile; 16-byte chunks
+__device__ __forceinline__ void stage_tile(bf16* dst, const bf16* src, int ld, int L, int lane) {
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int chunk = lane + 32 * it, row = chunk >> 2, part = chunk & 3;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (row < L) v = *reinterpret_cast<const uint4*>(src + size_t(row) * ld + part * 8);
+    *reinterpret_cast<uint4*>(dst + row * kRow + part * 8) = v;
+  }
+}
+
+// scores -> probabilities in the C-fragment layout.  s[mt][nt][e]: row 16*mt + g + 8*(e>>1), col 8*nt + 2*t + (e&1)
+__device__ __forceinline__ void softmax_rows(float (&s)[2][4][4], uint32_t key_mask, int t) {
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int hrow = 0; hrow < 2; ++hrow) {
+      float m = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = 8 * nt + 2 * t + e;
+          float& x = s[mt][nt][2 * hrow + e];
+          if (!((key_mask >> j) & 1u)) x = -INFINITY;
+          m = fmaxf(m, x);
+        }
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+      float sum = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          float& x = s[mt][nt][2 * hrow + e];
+          x = __expf(x - m);
+          sum += x;
+        }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      const float inv = 1.f / sum;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) s[mt][nt][2 * hrow + e] *= inv;
+    }
+}
+
+// dropout multipliers in the same layout: 8 consecutive Philox words per (pair, row, t)
+__device__ __forceinline__ void dropout_tile(float (&mult)[2][4][4], const Dropout& d, unsigned long long pair, int g,
+                                             int t) {
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int hrow = 0; hrow < 2; ++hrow) {
+      const int i = 16 * mt + g + 8 * hrow;
+      const unsigned long long base4 = ((pair * 32 + i) * 4 + t) * 2;  // index of the first group of 4 words
+      uint4 w0 = dropout_words(d, base4), w1 = dropout_words(d, base4 + 1);
+      const uint32_t w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) mult[mt][nt][2 * hrow + e] = w[2 * nt + e] >= d.thr ? d.scale : 0.f;
+    }
+}
+
+__device__ __forceinline__ uint32_t key_mask_of(const uint8_t* valid, size_t row0, int L, int lane) {
+  bool ok = lane < L;
+  if (ok && valid != nullptr) ok = valid[row0 + lane] != 0;
+  return __ballot_sync(0xffffffffu, ok);
+}
+
+// S = Q K^T  (both tiles row-major [row][channel])
+__device__ __forceinline__ void qk_scores(float (&s)[2][4][4], uint32_t q_tile, uint32_t k_tile, int lane) {
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[mt][nt][e] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    uint32_t a[2][4];
+    load_a(a[0], q_tile, 0, ks, lane);
+    load_a(a[1], q_tile, 1, ks, lane);
+#pragma unroll
+    for (int np = 0; np < 2; ++np) {
+      uint32_t b[4];
+      load_b_nk(b, k_tile, np, ks, lane);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        mma_bf16(s[mt][2 * np], a[mt], b[0], b[1]);
+        mma_bf16(s[mt][2 * np + 1], a[mt], b[2], b[3]);
+      }
+    }
+  }
+}
+
+// C-fragment of a 32 x 32 matrix (keys on the column axis) -> A-fragments for a product over those columns
+__device__ __forceinline__ void c_to_a(uint32_t (&a)[4], const float (&c)[2][4][4], int mt, int ks) {
+  a[0] = pack_bf16(c[mt][2 * ks][0], c[mt][2 * ks][1]);
+  a[1] = pack_bf16(c[mt][2 * ks][2], c[mt][2 * ks][3]);
+  a[2] = pack_bf16(c[mt][2 * ks + 1][0], c[mt][2 * ks + 1][1]);
+  a[3] = pack_bf16(c[mt][2 * ks + 1][2], c[mt][2 * ks + 1][3]);
+}
+// out[32 x 32] = A(regs, from c_to_a) . Y   with Y row-major [k][n] in smem
+__device__ __forceinline__ void mul_regs_kn(float (&o)[2][4][4], const float (&p)[2][4][4], uint32_t y_tile, int lane) {
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[mt][nt][e] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    uint32_t a[2][4];
+    c_to_a(a[0], p, 0, ks);
+    c_to_a(a[1], p, 1, ks);
+#pragma unroll
+    for (int np = 0; np < 2; ++np) {
+      uint32_t b[4];
+      load_b_kn(b, y_tile, np, ks, lane);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        mma_bf16(o[mt][2 * np], a[mt], b[0], b[1]);
+        mma_bf16(o[mt][2 * np + 1], a[mt], b[2], b[3]);
+      }
+    }
+  }
+}
+// out[32 x 32] = Z^T . Y   with Z, Y row-major [k][.] in smem (contraction over the smem row index)
+__device__ __forceinline__ void mul_t_kn(float (&o)[2][4][4], uint32_t z_tile, uint32_t y_tile, int lane) {
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[mt][nt][e] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    uint32_t a[2][4];
+    load_a_t(a[0], z_tile, 0, ks, lane);
+    load_a_t(a[1], z_tile, 1, ks, lane);
+#pragma unroll
+    for (int np = 0; np < 2; ++np) {
+      uint32_t b[4];
+      load_b_kn(b, y_tile, np, ks, lane);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        mma_bf16(o[mt][2 * np], a[mt], b[0], b[1]);
+        mma_bf16(o[mt][2 * np + 1], a[mt], b[2], b[3]);
+      }
+    }
+  }
+}
+// store a C-fragment as bf16 to global rows [row0 + i] (i < L), 32 channels starting at dst
+__device__ __forceinline__ void store_c_global(bf16* dst, int ld, int L, const float (&c)[2][4][4], float mul, int g,
+                                               int t) {
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int hrow = 0; hrow < 2; ++hrow) {
+      const int i = 16 * mt + g + 8 * hrow;
+      if (i < L) {
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+          *reinterpret_cast<uint32_t*>(dst + size_t(i) * ld + 8 * nt + 2 * t) =
+              pack_bf16(c[mt][nt][2 * hrow] * mul, c[mt][nt][2 * hrow + 1] * mul);
+      }
+    }
+}
+__device__ __forceinline__ void store_c_smem(bf16* tile, const float (&c)[2][4][4], int g, int t) {
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int hrow = 0; hrow < 2; ++hrow) {
+      const int i = 16 * mt + g + 8 * hrow;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+        *reinterpret_cast<uint32_t*>(tile + i * kRow + 8 * nt + 2 * t) = pack_bf16(c[mt][nt][2 * hrow], c[mt][nt][2 * hrow + 1]);
+    }
+}
+
+constexpr int kMmaWarps = 4;
+
+__global__ void __launch_bounds__(kMmaWarps * 32) attn_mma_fwd_kernel(MmaAttnArgs a) {
+  __shared__ __align__(16) bf16 sm[kMmaWarps][3 * kTile];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int L = a.L, d = a.H * 32, ld = 3 * d;
+  bf16* Qs = sm[wib];
+  bf16* Ks = Qs + kTile;
+  bf16* Vs = Ks + kTile;
+  const uint32_t q_t = smem_addr(Qs), k_t = smem_addr(Ks), v_t = smem_addr(Vs);
+  const long long npairs = (long long)a.nseq * a.H;
+  for (long long pair = (long long)blockIdx.x * kMmaWarps + wib; pair < npairs; pair += (long long)gridDim.x * kMmaWarps) {
+    const int seq = int(pair / a.H), h = int(pair % a.H);
+    const size_t row0 = size_t(seq) * L;
+    const bf16* base = a.qkv + row0 * ld + h * 32;
+    stage_tile(Qs, base, ld, L, lane);
+    stage_tile(Ks, base + d, ld, L, lane);
+    stage_tile(Vs, base + 2 * d, ld, L, lane);
+    const uint32_t kmask = key_mask_of(a.valid, row0, L, lane);
+    __syncwarp();
+    float s[2][4][4];
+    qk_scores(s, q_t, k_t, lane);
+    softmax_rows(s, kmask, t);
+    if (a.drop.p > 0.f) {
+      float mult[2][4][4];
+      dropout_tile(mult, a.drop, (unsigned long long)pair, g, t);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) s[mt][nt][e] *= mult[mt][nt][e];
+    }
+    float o[2][4][4];
+    mul_regs_kn(o, s, v_t, lane);
+    store_c_global(a.out + row0 * d + h * 32, d, L, o, 1.f, g, t);
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(kMmaWarps * 32) attn_mma_bwd_kernel(MmaAttnArgs a) {
+  extern __shared__ __align__(16) bf16 sm_dyn[];   // kMmaWarps x 6 tiles (60 KB: above the static limit)
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int L = a.L, d = a.H * 32, ld = 3 * d;
+  bf16* Qs = sm_dyn + wib * 6 * kTile;
+  bf16* Ks = Qs + kTile;
+  bf16* Vs = Ks + kTile;
+  bf16* Gs = Vs + kTile;   // dO
+  bf16* Ps = Gs + kTile;   // dropout-scaled probabilities
+  bf16* Ds = Ps + kTile;   // dS
+  const uint32_t q_t = smem_addr(Qs), k_t = smem_addr(Ks), v_t = smem_addr(Vs), g_t = smem_addr(Gs),
+                 p_t = smem_addr(Ps), d_t = smem_addr(Ds);
+  const long long npairs = (long long)a.nseq * a.H;
+  for (long long pair = (long long)blockIdx.x * kMmaWarps + wib; pair < npairs; pair += (long long)gridDim.x * kMmaWarps) {
+    const int seq = int(pair / a.H), h = int(pair % a.H);
+    const size_t row0 = size_t(seq) * L;
+    const bf16* base = a.qkv + row0 * ld + h * 32;
+    stage_tile(Qs, base, ld, L, lane);
+    stage_tile(Ks, base + d, ld, L, lane);
+    stage_tile(Vs, base + 2 * d, ld, L, lane);
+    stage_tile(Gs, a.dout + row0 * d + h * 32, d, L, lane);
+    const uint32_t kmask = key_mask_of(a.valid, row0, L, lane);
+    __syncwarp();
+    float p[2][4][4], dp[2][4][4];
+    qk_scores(p, q_t, k_t, lane);
+    softmax_rows(p, kmask, t);
+    qk_scores(dp, g_t, v_t, lane);            // dP = dO . V^T  (same operand shapes as Q . K^T)
+    if (a.drop.p > 0.f) {
+      float mult[2][4][4];
+      dropout_tile(mult, a.drop, (unsigned long long)pair, g, t);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            dp[mt][nt][e] *= mult[mt][nt][e];   // d loss / d p  (through the dropout)
+            mult[mt][nt][e] *= p[mt][nt][e];    // dropout-scaled probability (operand of dV)
+          }
+      store_c_smem(Ps, mult, g, t);
+    } else {
+      store_c_smem(Ps, p, g, t);
+    }
+    // dS = P o (dP - rowsum(dP o P))
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int hrow = 0; hrow < 2; ++hrow) {
+        float delta = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) delta = fmaf(dp[mt][nt][2 * hrow + e], p[mt][nt][2 * hrow + e], delta);
+        delta += __shfl_xor_sync(0xffffffffu, delta, 1);
+        delta += __shfl_xor_sync(0xffffffffu, delta, 2);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+            dp[mt][nt][2 * hrow + e] = p[mt][nt][2 * hrow + e] * (dp[mt][nt][2 * hrow + e] - delta);
+      }
+    store_c_smem(Ds, dp, g, t);
+    __syncwarp();
+    float o[2][4][4];
+    bf16* dbase = a.dqkv + row0 * ld + h * 32;
+    mul_regs_kn(o, dp, k_t, lane);                 // dQ = dS . K
+    store_c_global(dbase, ld, L, o, a.scale, g, t);
+    mul_t_kn(o, d_t, q_t, lane);                   // dK = dS^T . Q
+    store_c_global(dbase + d, ld, L, o, 1.f, g, t);
+    mul_t_kn(o, p_t, g_t, lane);                   // dV = (dropout(P))^T . dO
+    store_c_global(dbase + 2 * d, ld, L, o, 1.f, g, t);
+    __syncwarp();
+  }
+}
+
+}  // namespace dsvg
+using namespace dsvg;
+
+// Entry points used by attention.cu's dispatcher (not part of the public header: same ABI functions, faster path).
+int dsvg_attn_mma_fwd(const bf16* qkv, const uint8_t* valid, bf16* out, int nseq, int L, int H, Dropout drop,
+                      cudaStream_t st) {
+  MmaAttnArgs a{};
+  a.qkv = qkv; a.valid = valid; a.out = out; a.nseq = nseq; a.L = L; a.H = H; a.scale = 1.f; a.drop = drop;
+  long long blocks = ((long long)nseq * H + kMmaWarps - 1) / kMmaWarps;
+  if (blocks > 148LL * 32) blocks = 148LL * 32;
+  attn_mma_fwd_kernel<<<int(blocks), kMmaWarps * 32, 0, st>>>(a);
+  ++g_launches;
+  DSVG_LAUNCH_CHECK();
+  return 0;
+}
+int dsvg_attn_mma_bwd(const bf16* qkv, const uint8_t* valid, const bf16* dout, bf16* dqkv, int nseq, int L, int H,
+                      float q_scale, Dropout drop, cudaStream_t st) {
+  MmaAttnArgs a{};
+  a.qkv = qkv; a.valid = valid; a.dout = dout; a.dqkv = dqkv; a.nseq = nseq; a.L = L; a.H = H; a.scale = q_scale;
+  a.drop = drop;
+  long long blocks = ((long long)nseq * H + kMmaWarps - 1) / kMmaWarps;
+  if (blocks > 148LL * 32) blocks = 148LL * 32;
+  constexpr int smem = kMmaWarps * 6 * kTile * 2;
+  static bool configured = false;
+  if (!configured) {
+    DSVG_CUDA(cudaFuncSetAttribute(attn_mma_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  attn_mma_bwd_kernel<<<int(blocks), kMmaWarps * 32, smem, st>>>(a);
+  ++g_launches;
+  DSVG_LAUNCH_CHECK();
+  return 0;
+}

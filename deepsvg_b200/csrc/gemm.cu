@@ -12,6 +12,7 @@
 // Parity mode ("bf16x3"): operands carry a second bf16 plane (lo = v - bf16(v)); the issuer runs three products
 // per K step (hi*hi + hi*lo + lo*hi) into the same accumulator.  Same kernel, NPLANES = 2.
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
@@ -249,6 +250,26 @@ template <bool kOuter>
 __device__ __forceinline__ void epilogue_chunk(uint32_t (&v)[32], uint32_t stage_addr, int lane, long long row0, int col0,
                                                int M, int N, const Epi& ep, float alpha, float* C, int ldc) {
   const float acc_scale = (!kOuter && ep.acc_scale_dev != nullptr) ? __ldg(ep.acc_scale_dev) : 1.f;
+  if constexpr (!kOuter) {
+    if (ep.vec == 2) {
+      // direct path: thread = row, eight aligned 4-column groups straight from the TMEM registers (no smem round trip)
+      const long long row = row0 + lane;
+      if (row < M) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int col = col0 + 4 * q;
+          if (col < N) {
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ep.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
+            epi_vec4(make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                                 __uint_as_float(v[4 * q + 3])),
+                     row, col, N, ep, b4, acc_scale);
+          }
+        }
+      }
+      return;
+    }
+  }
   {
     const uint32_t my = stage_addr + lane * (kStageRow * 4);
 #pragma unroll
@@ -292,19 +313,23 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&v)[32], uint32_t stage
 // ------------------------------------------------------------------------------------------------
 // dsvg_linear kernel
 // ------------------------------------------------------------------------------------------------
+constexpr int kLinThreads = 320;    // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
+constexpr int kLinEpiWarps = 8;
+
 template <int BN, int NPLANES>
 struct LinearCfg {
   static constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB
   static constexpr int kBBytes = BN * kBlockK * 2;       // 16/32 KB
   static constexpr int kStageBytes = NPLANES * (kABytes + kBBytes);
-  static constexpr int kStages = (NPLANES == 1) ? 4 : 2;
+  static constexpr int kStagingBytes = kLinEpiWarps * kStageWarpBytes;
+  static constexpr int kStages = (212 * 1024 - kStagingBytes) / kStageBytes > 4 ? 4 : (212 * 1024 - kStagingBytes) / kStageBytes;
+  static_assert(kStages >= 2, "linear: at least two pipeline stages must fit");
   static constexpr int kTmemCols = 2 * BN;  // two accumulator stages (256 or 512: powers of two)
-  static constexpr int kStagingBytes = 4 * kStageWarpBytes;
   static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kStagingBytes + 256;
 };
 
 template <int BN, int NPLANES>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kLinThreads, 1)
 linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo, int M, int N, int K,
               Epi ep) {
@@ -336,7 +361,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);
+      mbar_init(&tempty_bar[a], kLinEpiWarps);
     }
     fence_barrier_init();
   }
@@ -429,8 +454,9 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       }
     }
   } else {
-    // =================== epilogue warps (2..5) ===================
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+    // =================== epilogue warps (2..9) ===================
+    const int quarter = warp & 3;         // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;     // which of the two column-chunk parities this warp drains
     const uint32_t stage_buf = smem_u32(staging) + (warp - 2) * kStageWarpBytes;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -442,7 +468,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       tc_fence_after();
       const long long row0 = (long long)m0 + quarter * 32;
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = half * 32; c < BN; c += 64) {
         if (n0 + c >= N) break;
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * BN + c), v);
@@ -474,22 +500,25 @@ struct OuterCfg {
   static constexpr int kBBytes = (BQ / 64) * kBoxBytes;         // BQ Q columns
   static constexpr int kStageBytes = NPLANES * (kABytes + kBBytes);
   static constexpr int kStages = (NPLANES == 1) ? 4 : 2;
-  static constexpr int kTmemCols = BQ;
+  static constexpr int kTmemCols = 2 * BQ;  // BQ accumulator columns + 32 for the column-sum (bias) tile, power of 2
+  static constexpr int kOnesBytes = 2048;   // 16 K-rows x 128 B of bf16 1.0: B operand of the column-sum MMA
   static constexpr int kStagingBytes = 4 * kStageWarpBytes;
-  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kStagingBytes + 256;
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kOnesBytes + kStagingBytes + 256;
 };
 
 template <int BQ, int NPLANES>
 __global__ void __launch_bounds__(kThreads, 1)
 outer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
              const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo, int M, int P, int Q,
-             int mblk_per_split, float alpha, const float* alpha_dev, float* C, int ldc, uint32_t lbo, uint32_t sbo) {
+             int mblk_per_split, float alpha, const float* alpha_dev, float* C, int ldc, float* colsum_out,
+             uint32_t lbo, uint32_t sbo) {
   using Cfg = OuterCfg<BQ, NPLANES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* tiles = smem;
-  float* staging = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kStagingBytes);
+  uint8_t* ones = smem + Cfg::kStages * Cfg::kStageBytes;  // 1024-aligned
+  float* staging = reinterpret_cast<float*>(ones + Cfg::kOnesBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ones + Cfg::kOnesBytes + Cfg::kStagingBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + Cfg::kStages;
   uint64_t* tfull_bar = bars + 2 * Cfg::kStages;
@@ -512,12 +541,16 @@ outer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     tmem_alloc(tmem_slot, Cfg::kTmemCols);
     tmem_relinquish();
   }
+  // bf16 1.0 everywhere: the layout of an all-ones operand is irrelevant, only the descriptor must be valid
+  for (int i = threadIdx.x; i < Cfg::kOnesBytes / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;
+  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int q_tiles = (Q + BQ - 1) / BQ;
+  const bool do_colsum = colsum_out != nullptr && (blockIdx.x % q_tiles) == 0;
   const int p0 = (blockIdx.x / q_tiles) * 128;
   const int q0 = (blockIdx.x % q_tiles) * BQ;
   const int total_mblk = (M + 63) / 64;
@@ -585,6 +618,15 @@ outer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             umma_f16(tmem_base, ad, bd, idesc, 1u);
           }
         }
+        if (do_colsum) {
+          constexpr uint32_t idesc1 = umma_idesc_bf16(128, 16, 1, 1);
+          const uint64_t od = umma_smem_desc(smem_u32(ones), lbo, sbo);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma_f16(tmem_base + BQ, umma_smem_desc(a_hi + k * 2048, lbo, sbo), od, idesc1, (i | k) != 0 ? 1u : 0u);
+            if (NPLANES == 2) umma_f16(tmem_base + BQ, umma_smem_desc(a_lo + k * 2048, lbo, sbo), od, idesc1, 1u);
+          }
+        }
         umma_commit(&empty_bar[stage]);
         if (++stage == Cfg::kStages) {
           stage = 0;
@@ -607,6 +649,13 @@ outer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(c), v);
       tmem_ld_wait();
       epilogue_chunk<true>(v, stage_buf, lane, (long long)p0 + quarter * 32, q0 + c, P, Q, dummy, alpha, C, ldc);
+    }
+    if (do_colsum) {  // column 0 of the [128 x 16] tile = sum over this CTA's rows of A[:, p]
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(BQ), v);
+      tmem_ld_wait();
+      const int prow = p0 + quarter * 32 + lane;
+      if (prow < P) atomicAdd(colsum_out + prow, __uint_as_float(v[0]) * alpha);
     }
   }
 
@@ -642,7 +691,7 @@ static int launch_linear(const CUtensorMap& a, const CUtensorMap& alo, const CUt
   }
   const int tiles = ceil_div(M, kBlockM) * ceil_div(N, BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  linear_kernel<BN, NPLANES><<<grid, kThreads, Cfg::kSmemBytes, st>>>(a, alo, b, blo, M, N, K, ep);
+  linear_kernel<BN, NPLANES><<<grid, kLinThreads, Cfg::kSmemBytes, st>>>(a, alo, b, blo, M, N, K, ep);
   ++g_launches;
   DSVG_LAUNCH_CHECK();
   return 0;
@@ -650,7 +699,8 @@ static int launch_linear(const CUtensorMap& a, const CUtensorMap& alo, const CUt
 
 template <int BQ, int NPLANES>
 static int launch_outer(const CUtensorMap& a, const CUtensorMap& alo, const CUtensorMap& b, const CUtensorMap& blo,
-                        int M, int P, int Q, float alpha, const float* alpha_dev, float* C, int ldc, cudaStream_t st) {
+                        int M, int P, int Q, float alpha, const float* alpha_dev, float* C, int ldc, float* colsum_out,
+                        cudaStream_t st) {
   using Cfg = OuterCfg<BQ, NPLANES>;
   static bool configured = false;
   if (!configured) {
@@ -666,7 +716,7 @@ static int launch_outer(const CUtensorMap& a, const CUtensorMap& alo, const CUte
   const int per = ceil_div(total_mblk, splits);
   splits = ceil_div(total_mblk, per);
   dim3 grid(out_tiles, splits);
-  outer_kernel<BQ, NPLANES><<<grid, kThreads, Cfg::kSmemBytes, st>>>(a, alo, b, blo, M, P, Q, per, alpha, alpha_dev, C, ldc,
+  outer_kernel<BQ, NPLANES><<<grid, kThreads, Cfg::kSmemBytes, st>>>(a, alo, b, blo, M, P, Q, per, alpha, alpha_dev, C, ldc, colsum_out,
                                                                       g_outer_lbo ? g_outer_lbo : Cfg::kBoxBytes,
                                                                       g_outer_sbo ? g_outer_sbo : 1024u);
   ++g_launches;
@@ -721,9 +771,11 @@ extern "C" int dsvg_linear(const dsvg_bf16* X, size_t x_lo_off, int lda, const d
     v = v && (!ep.rowvec || ep.rowvec_ld % 4 == 0) && (!ep.residual || ep.res_ld % 4 == 0) &&
         (!ep.out_f32 || ep.out_f32_ld % 4 == 0) && (!ep.mask || (ep.mask_ld % 4 == 0 && ep.mask_lo_off % 4 == 0)) &&
         (!ep.out_act || (ep.out_act_ld % 4 == 0 && ep.out_lo_off % 4 == 0));
-    ep.vec = v ? 1 : 0;
+    static const int direct = [] { const char* e = getenv("DSVG_EPI"); return (e && e[0] == 'd') ? 1 : 0; }();  // staged (transposed) epilogue measured 2.2x faster than direct
+    ep.vec = v ? (direct ? 2 : 1) : 0;
   }
-  const bool wide = (N > 128);
+  const bool split = x_lo_off != 0;
+  const bool wide = (N > 128) && !split;  // parity mode always uses the 128-wide tile (shared-memory budget)
   const uint32_t bn = wide ? 256 : 128;
   CUtensorMap a, alo, b, blo;
   const bf16* Xb = reinterpret_cast<const bf16*>(X);
@@ -732,20 +784,19 @@ extern "C" int dsvg_linear(const dsvg_bf16* X, size_t x_lo_off, int lda, const d
   if (make_map(&b, Wb, K, N, ldb, 64, bn)) return 1;
   alo = a;
   blo = b;
-  const bool split = x_lo_off != 0;
   if (split) {
     if (make_map(&alo, Xb + x_lo_off, K, M, lda, 64, 128)) return 1;
     if (make_map(&blo, Wb + w_lo_off, K, N, ldb, 64, bn)) return 1;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (wide) return split ? launch_linear<256, 2>(a, alo, b, blo, M, N, K, ep, st)
-                         : launch_linear<256, 1>(a, alo, b, blo, M, N, K, ep, st);
-  return split ? launch_linear<128, 2>(a, alo, b, blo, M, N, K, ep, st)
-               : launch_linear<128, 1>(a, alo, b, blo, M, N, K, ep, st);
+  if (split) return launch_linear<128, 2>(a, alo, b, blo, M, N, K, ep, st);
+  return wide ? launch_linear<256, 1>(a, alo, b, blo, M, N, K, ep, st)
+              : launch_linear<128, 1>(a, alo, b, blo, M, N, K, ep, st);
 }
 
 extern "C" int dsvg_outer(const dsvg_bf16* A, size_t a_lo_off, int lda, const dsvg_bf16* B, size_t b_lo_off, int ldb,
-                          int M, int P, int Q, float alpha, const float* alpha_dev, float* C, int ldc, void* stream) {
+                          int M, int P, int Q, float alpha, const float* alpha_dev, float* C, int ldc, float* colsum_out,
+                          void* stream) {
   DSVG_CHECK(A && B && C, "dsvg_outer: null pointer");
   DSVG_CHECK(M > 0 && P > 0 && Q > 0, "dsvg_outer: bad shape");
   DSVG_CHECK(lda % 8 == 0 && ldb % 8 == 0, "dsvg_outer: lda/ldb must be multiples of 8");
@@ -765,8 +816,8 @@ extern "C" int dsvg_outer(const dsvg_bf16* A, size_t a_lo_off, int lda, const ds
     if (make_map(&blo, Bb + b_lo_off, Q, M, ldb, 64, 64)) return 1;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (wide) return split ? launch_outer<256, 2>(a, alo, b, blo, M, P, Q, alpha, alpha_dev, C, ldc, st)
-                         : launch_outer<256, 1>(a, alo, b, blo, M, P, Q, alpha, alpha_dev, C, ldc, st);
-  return split ? launch_outer<128, 2>(a, alo, b, blo, M, P, Q, alpha, alpha_dev, C, ldc, st)
-               : launch_outer<128, 1>(a, alo, b, blo, M, P, Q, alpha, alpha_dev, C, ldc, st);
+  if (wide) return split ? launch_outer<256, 2>(a, alo, b, blo, M, P, Q, alpha, alpha_dev, C, ldc, colsum_out, st)
+                         : launch_outer<256, 1>(a, alo, b, blo, M, P, Q, alpha, alpha_dev, C, ldc, colsum_out, st);
+  return split ? launch_outer<128, 2>(a, alo, b, blo, M, P, Q, alpha, alpha_dev, C, ldc, colsum_out, st)
+               : launch_outer<128, 1>(a, alo, b, blo, M, P, Q, alpha, alpha_dev, C, ldc, colsum_out, st);
 }

@@ -591,13 +591,11 @@ class SVGTransformer(nn.Module):
         G = lambda n: gd[pre + "." + n]
         pff = self._drop(sv, pre + ".dropff")
         # ---- FFN ----
-        ops.colsum(dx2_act, M, d, G("linear2.bias"))
-        ops.outer(dx2_act, s["h"], M, d, ff, G("linear2.weight"))
+        ops.outer(dx2_act, s["h"], M, d, ff, G("linear2.weight"), colsum=G("linear2.bias"))
         dh = Act(M, ff, pl, dev)
         _, w2t = self._pack(pre + ".linear2.weight")
         ops.linear(dx2_act, w2t, M, ff, d, mask=s["h"], mask_scale=1.0 / (1.0 - pff[0]) if pff[0] > 0 else 1.0, out_act=dh)
-        ops.colsum(dh, M, ff, G("linear1.bias"))
-        ops.outer(dh, s["b"], M, ff, d, G("linear1.weight"))
+        ops.outer(dh, s["b"], M, ff, d, G("linear1.weight"), colsum=G("linear1.bias"))
         db = Act(M, d, pl, dev)
         _, w1t = self._pack(pre + ".linear1.weight")
         ops.linear(dh, w1t, M, d, ff, out_act=db)
@@ -606,15 +604,13 @@ class SVGTransformer(nn.Module):
         ops.ln_bwd(s["x1"], s["mean2"], s["rstd2"], P("norm2.weight"), M, d, dy=db, dx_in=dx2, dx_out=dx1, dact=dt,
                    drop=self._drop(sv, pre + ".drop1"), dgamma=G("norm2.weight"), dbeta=G("norm2.bias"))
         # ---- attention ----
-        ops.colsum(dt, M, d, G("self_attn.out_proj.bias"))
-        ops.outer(dt, s["o"], M, d, d, G("self_attn.out_proj.weight"))
+        ops.outer(dt, s["o"], M, d, d, G("self_attn.out_proj.weight"), colsum=G("self_attn.out_proj.bias"))
         do = Act(M, d, pl, dev)
         _, wot = self._pack(pre + ".self_attn.out_proj.weight")
         ops.linear(dt, wot, M, d, d, out_act=do)
         dqkv = Act(M, 3 * d, pl, dev)
         ops.attn_bwd(s["qkv"], key_valid, do, dqkv, nseq, L, H, hd, float(hd) ** -0.5, self._drop(sv, pre + ".attn"))
-        ops.colsum(dqkv, M, 3 * d, G("self_attn.in_proj_bias"))
-        ops.outer(dqkv, s["a"], M, 3 * d, d, G("self_attn.in_proj_weight"))
+        ops.outer(dqkv, s["a"], M, 3 * d, d, G("self_attn.in_proj_weight"), colsum=G("self_attn.in_proj_bias"))
         da = Act(M, d, pl, dev)
         _, wit = self._pack(pre + ".self_attn.in_proj_weight")
         ops.linear(dqkv, wit, M, d, 3 * d, out_act=da)
@@ -634,8 +630,8 @@ class SVGTransformer(nn.Module):
             ops.seg_sum(dx1, n_groups, L, d, out_f32=dgv)
             dg = Act(n_groups, d, pl, dev)
             ops.cast_act(dgv, n_groups, d, out=dg, drop=self._drop(sv, pre + ".dropg"))
-            ops.colsum(dg, n_groups, d, gd[pre + ".linear_global.bias"])
-            ops.outer(dg, zmem, n_groups, d, cfg.dim_z, gd[pre + ".linear_global.weight"])
+            ops.outer(dg, zmem, n_groups, d, cfg.dim_z, gd[pre + ".linear_global.weight"],
+                      colsum=gd[pre + ".linear_global.bias"])
             _, wt = self._pack(pre + ".linear_global.weight")
             ops.linear(dg, wt, n_groups, cfg.dim_z, d, residual=dzmem, out_f32=dzmem)
             if lab is not None:
@@ -652,8 +648,8 @@ class SVGTransformer(nn.Module):
         if lab is not None:
             dg2 = Act(N, d, pl, dev)
             ops.cast_act(d2v, N, d, out=dg2, drop=self._drop(sv, pre + ".dropg2"))
-            ops.colsum(dg2, N, d, gd[pre + ".linear_global2.bias"])
-            ops.outer(dg2, lab, N, d, cfg.dim_label, gd[pre + ".linear_global2.weight"])
+            ops.outer(dg2, lab, N, d, cfg.dim_label, gd[pre + ".linear_global2.weight"],
+                      colsum=gd[pre + ".linear_global2.bias"])
             _, wt = self._pack(pre + ".linear_global2.weight")
             ops.linear(dg2, wt, N, cfg.dim_label, d, residual=dlab, out_f32=dlab)
 
@@ -673,8 +669,7 @@ class SVGTransformer(nn.Module):
         gradient is accumulated into the fp32 buffer dy32 [M, d]."""
         _, wt = self._pack(name + ".weight")
         for dl, sc in sources:
-            ops.colsum(dl, M, n_out, gd[name + ".bias"], alpha_dev=sc)
-            ops.outer(dl, y, M, n_out, d, gd[name + ".weight"], alpha_dev=sc)
+            ops.outer(dl, y, M, n_out, d, gd[name + ".weight"], alpha_dev=sc, colsum=gd[name + ".bias"])
             ops.linear(dl, wt, M, d, n_out, acc_scale=sc, residual=dy32, out_f32=dy32)
 
     def _backward_impl(self, sv, out_grads, g_token):

@@ -16,6 +16,29 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# Optional launch profiler (bench.py): when PROFILE is a list, linear/outer/attention launches are bracketed by CUDA
+# events on the launching stream and recorded as (family, algorithmic flops, start event, end event).
+PROFILE = None
+
+
+class _Prof:
+    def __init__(self, family, flops):
+        self.family, self.flops = family, flops
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *a):
+        if PROFILE is not None:
+            self.e1.record()
+            PROFILE.append((self.family, self.flops, self.e0, self.e1))
+        return False
+
+
 def _p(t):
     return 0 if t is None else t.data_ptr()
 
@@ -72,14 +95,16 @@ def linear(X, W, M, N, K, *, bias=None, scale_cols=0, scale=1.0, relu=False, dro
         ep.out_f32, ep.out_f32_ld = out_f32.data_ptr(), out_f32.stride(0)
     if out_act is not None:
         ep.out_act, ep.out_lo_off, ep.out_act_ld = out_act.ptr, out_act.lo, out_act.ld
-    rc = _lib.load().dsvg_linear(X.ptr, X.lo, X.ld, W.ptr, W.lo, W.ld, M, N, K, C.byref(ep), _stream())
+    with _Prof("linear", 2.0 * M * N * K):
+        rc = _lib.load().dsvg_linear(X.ptr, X.lo, X.ld, W.ptr, W.lo, W.ld, M, N, K, C.byref(ep), _stream())
     _lib.check(rc, "dsvg_linear")
 
 
-def outer(A, B, M, P, Q, Cout, *, alpha=1.0, alpha_dev=None):
-    """Cout[P,Q] += alpha * A[M,P]^T . B[M,Q]; Cout fp32 (row stride = Cout.stride(0))."""
-    rc = _lib.load().dsvg_outer(A.ptr, A.lo, A.ld, B.ptr, B.lo, B.ld, M, P, Q, alpha, _p(alpha_dev), Cout.data_ptr(),
-                                Cout.stride(0), _stream())
+def outer(A, B, M, P, Q, Cout, *, alpha=1.0, alpha_dev=None, colsum=None):
+    """Cout[P,Q] += alpha * A[M,P]^T . B[M,Q]; Cout fp32 (row stride = Cout.stride(0)); colsum[P] += alpha * sum_rows A."""
+    with _Prof("outer", 2.0 * M * P * Q):
+        rc = _lib.load().dsvg_outer(A.ptr, A.lo, A.ld, B.ptr, B.lo, B.ld, M, P, Q, alpha, _p(alpha_dev),
+                                    Cout.data_ptr(), Cout.stride(0), _p(colsum), _stream())
     _lib.check(rc, "dsvg_outer")
 
 
@@ -148,14 +173,16 @@ def ln_bwd(x, mean, rstd, gamma, M, D, *, dy=None, dz=None, valid=None, inv_cnt=
 
 
 def attn_fwd(qkv, key_valid, out, nseq, L, H, hd, drop):
-    rc = _lib.load().dsvg_attn_fwd(qkv.ptr, qkv.lo, _p(key_valid), out.ptr, out.lo, nseq, L, H, hd, drop[0], drop[1],
-                                   drop[2], _stream())
+    with _Prof("attn_fwd", 4.0 * nseq * L * L * H * hd):
+        rc = _lib.load().dsvg_attn_fwd(qkv.ptr, qkv.lo, _p(key_valid), out.ptr, out.lo, nseq, L, H, hd, drop[0],
+                                       drop[1], drop[2], _stream())
     _lib.check(rc, "dsvg_attn_fwd")
 
 
 def attn_bwd(qkv, key_valid, dout, dqkv, nseq, L, H, hd, q_scale, drop):
-    rc = _lib.load().dsvg_attn_bwd(qkv.ptr, qkv.lo, _p(key_valid), dout.ptr, dout.lo, dqkv.ptr, dqkv.lo, nseq, L, H, hd,
-                                   q_scale, drop[0], drop[1], drop[2], _stream())
+    with _Prof("attn_bwd", 8.0 * nseq * L * L * H * hd):
+        rc = _lib.load().dsvg_attn_bwd(qkv.ptr, qkv.lo, _p(key_valid), dout.ptr, dout.lo, dqkv.ptr, dqkv.lo, nseq, L, H,
+                                       hd, q_scale, drop[0], drop[1], drop[2], _stream())
     _lib.check(rc, "dsvg_attn_bwd")
 
 

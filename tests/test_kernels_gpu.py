@@ -90,10 +90,12 @@ def test_outer_matches_fp32(planes, M, P, Q):
     lda, ldb = (P + 7) // 8 * 8, (Q + 7) // 8 * 8
     aa, ba = ops.act_from_float(A, planes, ld=lda), ops.act_from_float(B, planes, ld=ldb)
     Cout = torch.ones(P, Q, device=DEV)
+    cs = torch.ones(P, device=DEV)
     sc = torch.tensor([2.0], device=DEV)
-    ops.outer(aa, ba, M, P, Q, Cout, alpha=0.5, alpha_dev=sc)
+    ops.outer(aa, ba, M, P, Q, Cout, alpha=0.5, alpha_dev=sc, colsum=cs)
     ref = (aa.float().double().t() @ ba.float().double()).float() + 1.0
     assert _rel(Cout, ref) < 2e-5
+    assert _rel(cs, aa.float().double().sum(0).float() + 1.0) < 2e-5   # fused bias-gradient column sums
     if planes == 2:
         assert _rel(Cout, (A.double().t() @ B.double()).float() + 1.0) < 3e-5
 
@@ -179,26 +181,61 @@ def test_attention_fwd_bwd(L, H, hd, masked):
     assert _rel(dqkv.float(), qv.grad) < 1e-4
 
 
-def test_attention_dropout_consistent_fwd_bwd():
+@pytest.mark.parametrize("L,masked", [(32, True), (31, False), (8, True), (17, True)])
+def test_attention_mma_fast_path(L, masked):
+    """Single-plane bf16, head_dim 32, L <= 32 -> the mma.sync kernel; P and dS are rounded to bf16 inside."""
+    ops = _ops()
+    H, hd, nseq = 8, 32, 61
+    d, M = H * hd, nseq * L
+    qa = ops.act_from_float(_rand(M, 3 * d, seed=1, scale=0.7), 1)
+    qv = qa.float().clone().requires_grad_(True)
+    valid = vmask = None
+    if masked:
+        lens = torch.randint(1, L + 1, (nseq,), generator=torch.Generator().manual_seed(3))
+        vmask = (torch.arange(L)[None, :] < lens[:, None]).to(DEV)
+        valid = vmask.to(torch.uint8).reshape(-1).contiguous()
+    out = ops.Act(M, d, 1, DEV)
+    ops.attn_fwd(qa, valid, out, nseq, L, H, hd, (0.0, 0, 0))
+    q, k, v = (t.reshape(nseq, L, H, hd).transpose(1, 2) for t in qv.split(d, dim=-1))
+    s = q @ k.transpose(-1, -2)
+    if masked:
+        s = s.masked_fill(~vmask[:, None, None, :], float("-inf"))
+    ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(M, d)
+    assert _rel(out.float(), ref.detach()) < 1.5e-2
+    da = ops.act_from_float(_rand(M, d, seed=5), 1)
+    ref.backward(da.float())
+    dqkv = ops.Act(M, 3 * d, 1, DEV)
+    ops.attn_bwd(qa, valid, da, dqkv, nseq, L, H, hd, 0.5, (0.0, 0, 0))
+    g = qv.grad.clone()
+    g[:, :d] *= 0.5
+    for lo, hi, nm in ((0, d, "dq"), (d, 2 * d, "dk"), (2 * d, 3 * d, "dv")):
+        e = (dqkv.float()[:, lo:hi] - g[:, lo:hi]).norm() / g[:, lo:hi].norm()
+        assert e.item() < 1.5e-2, (nm, e.item())
+
+
+@pytest.mark.parametrize("planes", [1, 2])
+def test_attention_dropout_consistent_fwd_bwd(planes):
     """With dropout the backward must use the forward's mask: check d(out . w)/dv against finite structure."""
     ops = _ops()
     nseq, L, H, hd = 5, 32, 8, 32
     d, M = H * hd, nseq * L
     qkv = _rand(M, 3 * d, seed=1, scale=0.5)
-    qa = ops.act_from_float(qkv, 2)
+    qa = ops.act_from_float(qkv, planes)
     drop = (0.3, 11, 99)
-    o1, o2 = ops.Act(M, d, 2, DEV), ops.Act(M, d, 2, DEV)
+    o1, o2 = ops.Act(M, d, planes, DEV), ops.Act(M, d, planes, DEV)
     ops.attn_fwd(qa, None, o1, nseq, L, H, hd, drop)
     ops.attn_fwd(qa, None, o2, nseq, L, H, hd, drop)
     assert torch.equal(o1.t, o2.t)
     # out is linear in v for fixed probabilities+mask: out(v) . g == v . dv(g)
     g = _rand(M, d, seed=2)
-    ga = ops.act_from_float(g, 2)
-    dqkv = ops.Act(M, 3 * d, 2, DEV)
+    ga = ops.act_from_float(g, planes)
+    dqkv = ops.Act(M, 3 * d, planes, DEV)
     ops.attn_bwd(qa, None, ga, dqkv, nseq, L, H, hd, 1.0, drop)
     lhs = (o1.float() * ga.float()).sum().item()
     rhs = (qa.float()[:, 2 * d:] * dqkv.float()[:, 2 * d:]).sum().item()
-    assert abs(lhs - rhs) < 2e-3 * abs(lhs)
+    assert abs(lhs - rhs) < (2e-3 if planes == 2 else 2e-2) * abs(lhs)
+    keep = (o1.float().abs() > 0).float().mean().item()   # dropped probabilities thin the output but never zero a row
+    assert keep > 0.99
 
 
 # ------------------------------------------------------------------------------------------------ embedding

@@ -1,0 +1,178 @@
+"""End-to-end parity on the GPU: deepsvg_b200.SVGTransformer + SVGLoss (CUDA, through the C ABI) against the CPU oracle
+(oracle/svg_oracle.py, itself pinned to the reference by tests/test_oracle_golden.py) and against the committed
+reference goldens, on the same seeded weights and inputs.
+
+Tolerances (BASELINE.json north_star): logits / loss rtol=1e-3, atol=1e-4 and bit-exact argmax in parity mode
+("bf16x3": split-bf16 operands on the same tcgen05 kernels).  Fast mode ("bf16", single-pass bf16 operands) cannot
+meet that end-to-end for ANY implementation (hard part 1); it is held to a looser, stated bound.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import svg_oracle as O
+from tests.golden_cases import load_case
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+W = dict(O.DEFAULT_WEIGHTS)
+
+
+def _build(cfg_o, precision, seed=7):
+    from deepsvg_b200 import SVGLoss, SVGTransformer
+    from deepsvg_b200.config import _DefaultConfig
+    cfg = _DefaultConfig(**{k: v for k, v in vars(cfg_o).items()})
+    model = SVGTransformer(cfg, precision=precision)
+    params = O.make_params(cfg_o, seed=seed)
+    missing, unexpected = model.load_state_dict(params, strict=False)
+    assert not unexpected and all(("position" in k or k == "cmd_args_mask") for k in missing)
+    return model.to(DEV).eval(), SVGLoss(cfg).to(DEV), params
+
+
+def _run(model, loss_fn, cmd, arg, label=None, eps=None):
+    model._eps_override = eps.to(DEV) if eps is not None else None
+    model.zero_grad(set_to_none=True)
+    out = model(cmd.to(DEV), arg.to(DEV), cmd.to(DEV), arg.to(DEV), label=None if label is None else label.to(DEV),
+                params={})
+    ls = loss_fn(out, None, weights=W)
+    ls["loss"].backward()
+    grads = {k: p.grad.detach().cpu() for k, p in model.named_parameters()}
+    return out, ls, grads
+
+
+def _check_grads(grads, ref, rel_tol):
+    worst = ("", 0.0)
+    for k, g in ref.items():
+        denom = g.norm().item() + 1e-12
+        e = (grads[k] - g).norm().item() / denom
+        if e > worst[1]:
+            worst = (k, e)
+        assert e < rel_tol, (k, e)
+    return worst
+
+
+CASES = {
+    "hier": ("hierarchical", dict(use_vae=False), 4),
+    "hier_vae_label": ("hierarchical", dict(use_vae=True, label_condition=True, n_labels=52, dim_z=128), 3),
+    "one_stage_fonts": ("one_stage", dict(use_vae=True, label_condition=True, n_labels=52, max_total_len=50), 5),
+    "small_d128": ("hierarchical", dict(use_vae=False, d_model=128, n_heads=4, dim_feedforward=256, dim_z=64, n_layers=2,
+                                        n_layers_decode=2, max_num_groups=4, max_seq_len=10), 6),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_parity_mode_matches_oracle(name):
+    kind, over, n = CASES[name]
+    cfg = O.make_cfg(kind, **over)
+    model, loss_fn, params = _build(cfg, "bf16x3")
+    cmd, arg = O.synth_batch(cfg, n, seed=21)
+    label = torch.randint(0, cfg.n_labels, (n,), generator=torch.Generator().manual_seed(2)) if cfg.label_condition else None
+    eps = torch.randn(n, cfg.dim_z, generator=torch.Generator().manual_seed(3)) if cfg.use_vae else None
+    out, ls, grads = _run(model, loss_fn, cmd, arg, label, eps)
+    ro, rl, rg = O.train_step(params, cfg, cmd, arg, label=label, eps=eps)
+    for k in ("command_logits", "args_logits", "visibility_logits", "mu", "logsigma"):
+        if k in ro:
+            got = out[k].detach().cpu()
+            assert got.shape == ro[k].shape, k
+            np.testing.assert_allclose(got.numpy(), ro[k].numpy(), rtol=1e-3, atol=1e-4, err_msg=k)
+    # bit-exact argmax of command / argument predictions
+    assert torch.equal(out["command_logits"].argmax(-1).cpu(), ro["command_logits"].argmax(-1))
+    assert torch.equal(out["args_logits"].argmax(-1).cpu(), ro["args_logits"].argmax(-1))
+    for k, v in rl.items():
+        assert abs(ls[k].item() - v.item()) <= 1e-3 * abs(v.item()) + 1e-4, (k, ls[k].item(), v.item())
+    # Gradients: split-bf16 operands carry 16 mantissa bits, so ~1e-5 of the ReLU pre-activations sit on the other side
+    # of zero than in fp32 and flip their mask; expected relative L2 error sqrt(n_flip / n) ~ 4e-3 on the tensors
+    # behind few rows (measured 3.6e-3 on decoder.decoder.layers.0.*; the CPU oracle run with matmul='bf16x3' shows
+    # the same 3.6e-3 on the same tensors -- see DESIGN.md 'Gradient tolerance').
+    _check_grads(grads, rg, 1e-2)
+
+
+def test_parity_mode_matches_reference_golden():
+    """BASELINE.json configs[0]: hierarchical_ordered, batch 2 -- against numbers produced by the reference itself."""
+    cfg, fx, _ = load_case("hier_cfg1")
+    model, loss_fn, _ = _build(cfg, "bf16x3", seed=int(fx["seed_params"]))
+    cmd, arg = torch.from_numpy(fx["commands"]), torch.from_numpy(fx["args"])
+    out, ls, grads = _run(model, loss_fn, cmd, arg)
+    idx = lambda t, n: t.reshape(-1)[torch.linspace(0, t.numel() - 1, n).long()]
+    for k in ("command_logits", "args_logits", "visibility_logits"):
+        got = idx(out[k].detach().cpu(), 4096) if out[k].numel() > 4096 else out[k].detach().cpu().reshape(-1)
+        np.testing.assert_allclose(got.numpy(), fx["O_" + k].reshape(-1), rtol=1e-3, atol=1e-4, err_msg=k)
+    for k in ("loss", "loss_cmd", "loss_args", "loss_visibility"):
+        assert abs(ls[k].item() - float(fx["L_" + k])) <= 1e-3 * float(fx["L_" + k]), k
+    for k, g in grads.items():
+        ref_norm = float(fx["Gnorm_" + k])
+        assert abs(g.double().norm().item() - ref_norm) <= 1e-2 * ref_norm + 1e-9, k
+
+
+def test_fast_mode_deviation_is_bounded():
+    """Single-pass bf16 operands: reported honestly, bounded loosely (loss within 1 %, logits within 0.05 abs,
+    argument argmax agreement > 97 %, gradients within 6 % relative L2)."""
+    kind, over, n = CASES["hier"]
+    cfg = O.make_cfg(kind, **over)
+    model, loss_fn, params = _build(cfg, "bf16")
+    cmd, arg = O.synth_batch(cfg, n, seed=21)
+    out, ls, grads = _run(model, loss_fn, cmd, arg)
+    ro, rl, rg = O.train_step(params, cfg, cmd, arg)
+    err = (out["args_logits"].detach().cpu() - ro["args_logits"]).abs().max().item()
+    agree = (out["args_logits"].argmax(-1).cpu() == ro["args_logits"].argmax(-1)).float().mean().item()
+    assert err < 0.05 and agree > 0.97, (err, agree)
+    assert abs(ls["loss"].item() - rl["loss"].item()) < 1e-2 * rl["loss"].item()
+    _check_grads(grads, rg, 6e-2)
+
+
+def test_train_mode_dropout_statistics_and_loss_api():
+    """train(): stochastic, seeded per call, finite; the loss dict has the reference's keys and .item() works."""
+    cfg = O.make_cfg("hierarchical", use_vae=True)
+    model, loss_fn, _ = _build(cfg, "bf16")
+    model.train()
+    cmd, arg = O.synth_batch(cfg, 4, seed=5)
+    c, a = cmd.to(DEV), arg.to(DEV)
+    o1 = model(c, a, c, a, params={})
+    o2 = model(c, a, c, a, params={})
+    assert not torch.equal(o1["args_logits"], o2["args_logits"])
+    ls = loss_fn(o1, None, weights=W)
+    assert set(ls) == {"loss", "loss_cmd", "loss_args", "loss_visibility", "loss_kl"}
+    ls["loss"].backward()
+    assert all(torch.isfinite(p.grad).all() for p in model.parameters())
+    assert all(np.isfinite(v.item()) for v in ls.values())
+    assert set(o1) == {"command_logits", "args_logits", "visibility_logits", "tgt_commands", "tgt_args", "mu", "logsigma"}
+    assert o1["args_logits"].shape == (4, 8, 31, 11, 257) and o1["visibility_logits"].shape == (4, 8, 1, 2)
+
+
+def test_generic_autograd_path_matches_fused_path():
+    """A user loss on the logits (no SVGLoss): gradients must flow through the explicit-gradient path."""
+    cfg = O.make_cfg("hierarchical", use_vae=False)
+    model, loss_fn, _ = _build(cfg, "bf16x3")
+    cmd, arg = O.synth_batch(cfg, 2, seed=9)
+    c, a = cmd.to(DEV), arg.to(DEV)
+    model.zero_grad(set_to_none=True)
+    out = model(c, a, c, a, params={})
+    ls = loss_fn(out, None, weights=W)
+    ls["loss"].backward()
+    g_fused = {k: p.grad.clone() for k, p in model.named_parameters()}
+    model.zero_grad(set_to_none=True)
+    out = model(c, a, c, a, params={})
+    O.CMD_ARGS_MASK = O.CMD_ARGS_MASK.to(DEV)
+    try:
+        plain = {k: (v if k.startswith("tgt") else v) for k, v in out.items()}
+        O.loss(plain, cfg, W)["loss"].backward()
+    finally:
+        O.CMD_ARGS_MASK = O.CMD_ARGS_MASK.cpu()
+    for k, p in model.named_parameters():
+        e = (p.grad - g_fused[k]).norm().item() / (g_fused[k].norm().item() + 1e-12)
+        assert e < 1e-2, (k, e)
+
+
+def test_encode_mode_and_z_injection():
+    cfg = O.make_cfg("hierarchical", use_vae=False)
+    model, _, params = _build(cfg, "bf16x3")
+    cmd, arg = O.synth_batch(cfg, 3, seed=4)
+    c, a = cmd.to(DEV), arg.to(DEV)
+    with torch.no_grad():
+        z = model(c, a, None, None, encode_mode=True)
+        assert z.shape == (1, 1, 3, cfg.dim_z)
+        ro = O.forward(params, cfg, cmd, arg)
+        np.testing.assert_allclose(z.view(3, -1).cpu().numpy(), ro["z"].numpy(), rtol=1e-3, atol=1e-4)
+        out = model(None, None, None, None, z=z.view(3, 1, 1, -1), return_tgt=False)
+        np.testing.assert_allclose(out["args_logits"].cpu().numpy(), ro["args_logits"].numpy(), rtol=1e-3, atol=1e-4)
+        assert "tgt_commands" not in out
