@@ -380,15 +380,15 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   const int num_kb = (K + kBlockK - 1) / kBlockK;
 
   if (warp == 0) {
-    // =================== TMA producer ===================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_tiles) * kBlockM;
-        const int n0 = (tile % n_tiles) * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    // =================== TMA producer (warp-uniform control flow, one elected lane issues) ===================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / n_tiles) * kBlockM;
+      const int n0 = (tile % n_tiles) * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           uint8_t* st = tiles + stage * Cfg::kStageBytes;
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           tma_load_2d(st, &tmA, &full_bar[stage], kb * kBlockK, m0);
@@ -397,60 +397,54 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             tma_load_2d(st + Cfg::kABytes + Cfg::kBBytes, &tmAlo, &full_bar[stage], kb * kBlockK, m0);
             tma_load_2d(st + 2 * Cfg::kABytes + Cfg::kBBytes, &tmBlo, &full_bar[stage], kb * kBlockK, n0);
           }
-          if (++stage == Cfg::kStages) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        __syncwarp();
+        if (++stage == Cfg::kStages) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
-    // =================== MMA issuer ===================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+    // =================== MMA issuer (warp-uniform control flow, one elected lane issues) ===================
+    constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
+        if (elect_one()) {
           const uint32_t a_hi = smem_u32(tiles + stage * Cfg::kStageBytes);
           const uint32_t b_hi = a_hi + Cfg::kABytes;
           const uint32_t a_lo = b_hi + Cfg::kBBytes;
           const uint32_t b_lo = a_lo + Cfg::kABytes;
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            uint64_t ad = umma_smem_desc(a_hi + k * 32, 16, 1024);
-            uint64_t bd = umma_smem_desc(b_hi + k * 32, 16, 1024);
-            umma_f16(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma_f16(d_tmem, umma_smem_desc(a_hi + k * 32, 16, 1024), umma_smem_desc(b_hi + k * 32, 16, 1024), idesc,
+                     (kb | k) != 0 ? 1u : 0u);
           if (NPLANES == 2) {
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k) {
-              uint64_t ad = umma_smem_desc(a_hi + k * 32, 16, 1024);
-              uint64_t bd = umma_smem_desc(b_lo + k * 32, 16, 1024);
-              umma_f16(d_tmem, ad, bd, idesc, 1u);
-            }
+            for (int k = 0; k < kBlockK / 16; ++k)
+              umma_f16(d_tmem, umma_smem_desc(a_hi + k * 32, 16, 1024), umma_smem_desc(b_lo + k * 32, 16, 1024), idesc, 1u);
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k) {
-              uint64_t ad = umma_smem_desc(a_lo + k * 32, 16, 1024);
-              uint64_t bd = umma_smem_desc(b_hi + k * 32, 16, 1024);
-              umma_f16(d_tmem, ad, bd, idesc, 1u);
-            }
+            for (int k = 0; k < kBlockK / 16; ++k)
+              umma_f16(d_tmem, umma_smem_desc(a_lo + k * 32, 16, 1024), umma_smem_desc(b_hi + k * 32, 16, 1024), idesc, 1u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
-          if (++stage == Cfg::kStages) {
-            stage = 0;
-            phase ^= 1;
-          }
+          umma_commit(&empty_bar[stage]);                      // frees the smem slot once these MMAs retire
+          if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete
+        __syncwarp();
+        if (++stage == Cfg::kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
     }
   } else {
@@ -500,8 +494,8 @@ struct OuterCfg {
   static constexpr int kBBytes = (BQ / 64) * kBoxBytes;         // BQ Q columns
   static constexpr int kStageBytes = NPLANES * (kABytes + kBBytes);
   static constexpr int kStages = (NPLANES == 1) ? 4 : 2;
-  static constexpr int kTmemCols = 2 * BQ;  // BQ accumulator columns + 32 for the column-sum (bias) tile, power of 2
-  static constexpr int kOnesBytes = 2048;   // 16 K-rows x 128 B of bf16 1.0: B operand of the column-sum MMA
+  static constexpr int kTmemCols = 2 * BQ;  // BQ accumulator columns + 64 for the column-sum (bias) tile, power of 2
+  static constexpr int kOnesBytes = 4096;   // 16 K-rows x 128 B of bf16 1.0 (B operand of the column-sum MMA) + slack
   static constexpr int kStagingBytes = 4 * kStageWarpBytes;
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kOnesBytes + kStagingBytes + 256;
 };
@@ -559,11 +553,11 @@ outer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int num_mb = mb_end - mb_begin;  // >= 1 by construction of the grid
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int mb = mb_begin; mb < mb_end; ++mb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int mb = mb_begin; mb < mb_end; ++mb) {
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      if (elect_one()) {
         uint8_t* st = tiles + stage * Cfg::kStageBytes;
         mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
 #pragma unroll
@@ -580,60 +574,56 @@ outer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           for (int j = 0; j < BQ / 64; ++j)
             tma_load_2d(lo + Cfg::kABytes + j * Cfg::kBoxBytes, &tmBlo, &full_bar[stage], q0 + 64 * j, mb * 64);
         }
-        if (++stage == Cfg::kStages) {
-          stage = 0;
-          phase ^= 1;
-        }
+      }
+      __syncwarp();
+      if (++stage == Cfg::kStages) {
+        stage = 0;
+        phase ^= 1;
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BQ, 1, 1);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int i = 0; i < num_mb; ++i) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
+    constexpr uint32_t idesc = umma_idesc_bf16(128, BQ, 1, 1);
+    constexpr uint32_t idesc1 = umma_idesc_bf16(128, 64, 1, 1);  // N = 64: one full 128-byte swizzle atom of ones per K row
+    const uint32_t ones_addr = smem_u32(ones);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int i = 0; i < num_mb; ++i) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
         const uint32_t a_hi = smem_u32(tiles + stage * Cfg::kStageBytes);
         const uint32_t b_hi = a_hi + Cfg::kABytes;
         const uint32_t a_lo = b_hi + Cfg::kBBytes;
         const uint32_t b_lo = a_lo + Cfg::kABytes;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {  // 16 rows (= 2 KB) of the 64-row block per UMMA
-          uint64_t ad = umma_smem_desc(a_hi + k * 2048, lbo, sbo);
-          uint64_t bd = umma_smem_desc(b_hi + k * 2048, lbo, sbo);
-          umma_f16(tmem_base, ad, bd, idesc, (i | k) != 0 ? 1u : 0u);
-        }
+        for (int k = 0; k < 4; ++k)  // 16 rows (= 2 KB) of the 64-row block per UMMA
+          umma_f16(tmem_base, umma_smem_desc(a_hi + k * 2048, lbo, sbo), umma_smem_desc(b_hi + k * 2048, lbo, sbo), idesc,
+                   (i | k) != 0 ? 1u : 0u);
         if (NPLANES == 2) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            uint64_t ad = umma_smem_desc(a_hi + k * 2048, lbo, sbo);
-            uint64_t bd = umma_smem_desc(b_lo + k * 2048, lbo, sbo);
-            umma_f16(tmem_base, ad, bd, idesc, 1u);
-          }
+          for (int k = 0; k < 4; ++k)
+            umma_f16(tmem_base, umma_smem_desc(a_hi + k * 2048, lbo, sbo), umma_smem_desc(b_lo + k * 2048, lbo, sbo), idesc, 1u);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            uint64_t ad = umma_smem_desc(a_lo + k * 2048, lbo, sbo);
-            uint64_t bd = umma_smem_desc(b_hi + k * 2048, lbo, sbo);
-            umma_f16(tmem_base, ad, bd, idesc, 1u);
-          }
+          for (int k = 0; k < 4; ++k)
+            umma_f16(tmem_base, umma_smem_desc(a_lo + k * 2048, lbo, sbo), umma_smem_desc(b_hi + k * 2048, lbo, sbo), idesc, 1u);
         }
         if (do_colsum) {
-          constexpr uint32_t idesc1 = umma_idesc_bf16(128, 16, 1, 1);
-          const uint64_t od = umma_smem_desc(smem_u32(ones), lbo, sbo);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            umma_f16(tmem_base + BQ, umma_smem_desc(a_hi + k * 2048, lbo, sbo), od, idesc1, (i | k) != 0 ? 1u : 0u);
-            if (NPLANES == 2) umma_f16(tmem_base + BQ, umma_smem_desc(a_lo + k * 2048, lbo, sbo), od, idesc1, 1u);
+            umma_f16(tmem_base + BQ, umma_smem_desc(a_hi + k * 2048, lbo, sbo), umma_smem_desc(ones_addr, lbo, sbo), idesc1,
+                     (i | k) != 0 ? 1u : 0u);
+            if (NPLANES == 2)
+              umma_f16(tmem_base + BQ, umma_smem_desc(a_lo + k * 2048, lbo, sbo), umma_smem_desc(ones_addr, lbo, sbo), idesc1, 1u);
           }
         }
         umma_commit(&empty_bar[stage]);
-        if (++stage == Cfg::kStages) {
-          stage = 0;
-          phase ^= 1;
-        }
+        if (i == num_mb - 1) umma_commit(tfull_bar);
       }
-      umma_commit(tfull_bar);
+      __syncwarp();
+      if (++stage == Cfg::kStages) {
+        stage = 0;
+        phase ^= 1;
+      }
     }
   } else {
     const int quarter = warp & 3;
@@ -650,7 +640,7 @@ outer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       tmem_ld_wait();
       epilogue_chunk<true>(v, stage_buf, lane, (long long)p0 + quarter * 32, q0 + c, P, Q, dummy, alpha, C, ldc);
     }
-    if (do_colsum) {  // column 0 of the [128 x 16] tile = sum over this CTA's rows of A[:, p]
+    if (do_colsum) {  // column 0 of the [128 x 64] tile = sum over this CTA's rows of A[:, p]
       uint32_t v[32];
       tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(BQ), v);
       tmem_ld_wait();

@@ -73,7 +73,7 @@ int dsvg_linear(const dsvg_bf16* X, size_t x_lo_off, int lda, const dsvg_bf16* W
 /* C[P,Q] += alpha * (*alpha_dev) * A[M,P]^T . B[M,Q]   (contraction over the M rows; A, B row-major act tensors;
  * alpha_dev optional DEVICE scalar).  fp32 atomic adds into C (the M range is split across CTAs), so C is the
  * gradient accumulator itself.  colsum_out (optional, [P]) += alpha * column sums of A, computed by one extra
- * [128 x 16] MMA against an all-ones operand: weight AND bias gradient of every F.linear above from one pass over
+ * [128 x 64] MMA against an all-ones operand: weight AND bias gradient of every F.linear above from one pass over
  * dY (autograd of the reference, loss.backward() at train.py:98). */
 int dsvg_outer(const dsvg_bf16* A, size_t a_lo_off, int lda, const dsvg_bf16* B, size_t b_lo_off, int ldb, int M,
                int P, int Q, float alpha, const float* alpha_dev, float* C, int ldc, float* colsum_out, void* stream);
