@@ -200,9 +200,30 @@ __device__ __forceinline__ void st_act4(bf16* p, size_t lo_off, size_t i, float4
   }
 }
 
+// Operands of the vector epilogue that come from global memory; loaded for all 8 row-iterations of a chunk BEFORE any
+// store is issued, so the (up to three) DRAM round trips of a chunk overlap instead of serialising per iteration.
+struct EpiLoads {
+  float4 res, rv;
+  uint2 mhi, mlo;
+};
+__device__ __forceinline__ float4 bf16x4_to_f4(uint2 u) {
+  float2 a = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u.x));
+  float2 b = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void epi_vec4_load(EpiLoads& l, long long row, int col, const Epi& ep) {
+  if (ep.rowvec != nullptr)
+    l.rv = __ldg(reinterpret_cast<const float4*>(ep.rowvec + (long long)(int(row) / ep.rows_per_group) * ep.rowvec_ld + col));
+  if (ep.mask != nullptr) {
+    const size_t mi = size_t(row) * ep.mask_ld + col;
+    l.mhi = *reinterpret_cast<const uint2*>(ep.mask + mi);
+    if (ep.mask_lo_off) l.mlo = *reinterpret_cast<const uint2*>(ep.mask + mi + ep.mask_lo_off);
+  }
+  if (ep.residual != nullptr) l.res = *reinterpret_cast<const float4*>(ep.residual + row * (long long)ep.res_ld + col);
+}
 // 4 consecutive columns of one row, all vector accesses aligned (host guarantees ep.vec preconditions)
 __device__ __forceinline__ void epi_vec4(float4 x, long long row, int col, int N, const Epi& ep, const float4& bias4,
-                                         float acc_scale) {
+                                         float acc_scale, const EpiLoads& l) {
   x.x *= acc_scale; x.y *= acc_scale; x.z *= acc_scale; x.w *= acc_scale;
   x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w;
   if (ep.scale_cols > 0) {
@@ -219,15 +240,13 @@ __device__ __forceinline__ void epi_vec4(float4 x, long long row, int col, int N
     x.x *= m.x; x.y *= m.y; x.z *= m.z; x.w *= m.w;
   }
   if (ep.rowvec != nullptr) {
-    float4 g = __ldg(reinterpret_cast<const float4*>(ep.rowvec + (long long)(int(row) / ep.rows_per_group) * ep.rowvec_ld + col));
-    x.x += g.x; x.y += g.y; x.z += g.z; x.w += g.w;
+    x.x += l.rv.x; x.y += l.rv.y; x.z += l.rv.z; x.w += l.rv.w;
   }
   if (ep.mask != nullptr) {
-    size_t mi = size_t(row) * ep.mask_ld + col;
-    float4 m = ld_bf16x4(ep.mask + mi);
+    float4 m = bf16x4_to_f4(l.mhi);
     if (ep.mask_lo_off) {
-      float4 l = ld_bf16x4(ep.mask + mi + ep.mask_lo_off);
-      m.x += l.x; m.y += l.y; m.z += l.z; m.w += l.w;
+      float4 lo = bf16x4_to_f4(l.mlo);
+      m.x += lo.x; m.y += lo.y; m.z += lo.z; m.w += lo.w;
     }
     x.x = m.x != 0.f ? x.x * ep.mask_scale : 0.f;
     x.y = m.y != 0.f ? x.y * ep.mask_scale : 0.f;
@@ -235,8 +254,7 @@ __device__ __forceinline__ void epi_vec4(float4 x, long long row, int col, int N
     x.w = m.w != 0.f ? x.w * ep.mask_scale : 0.f;
   }
   if (ep.residual != nullptr) {
-    float4 r = *reinterpret_cast<const float4*>(ep.residual + row * (long long)ep.res_ld + col);
-    x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
+    x.x += l.res.x; x.y += l.res.y; x.z += l.res.z; x.w += l.res.w;
   }
   if (ep.out_f32 != nullptr) *reinterpret_cast<float4*>(ep.out_f32 + row * (long long)ep.out_f32_ld + col) = x;
   if (ep.out_act != nullptr) st_act4(ep.out_act, ep.out_lo_off, size_t(row) * ep.out_act_ld + col, x);
@@ -261,9 +279,11 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&v)[32], uint32_t stage
           if (col < N) {
             float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (ep.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
+            EpiLoads l;
+            epi_vec4_load(l, row, col, ep);
             epi_vec4(make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
                                  __uint_as_float(v[4 * q + 3])),
-                     row, col, N, ep, b4, acc_scale);
+                     row, col, N, ep, b4, acc_scale, l);
           }
         }
       }
@@ -289,22 +309,47 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&v)[32], uint32_t stage
   } else if (ep.vec) {
     const int cg = lane & 7, rsub = lane >> 3;
     const int col = col0 + 4 * cg;
+    const bool col_ok = col < N;
     float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (ep.bias != nullptr && col < N) bias4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
-#pragma unroll 2
-    for (int i = 0; i < 8; ++i) {
-      const int rl = 4 * i + rsub;
-      float4 x = ld_shared_v4(stage_addr + (rl * kStageRow + 4 * cg) * 4);
-      long long row = row0 + rl;
-      if (row < M && col < N) epi_vec4(x, row, col, N, ep, bias4, acc_scale);
+    if (ep.bias != nullptr && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {   // two groups of four rows: 4 x (residual, mask, rowvec) loads in flight per group
+      EpiLoads ld[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const long long row = row0 + 4 * (4 * h + i) + rsub;
+        if (row < M && col_ok) epi_vec4_load(ld[i], row, col, ep);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int rl = 4 * (4 * h + i) + rsub;
+        float4 x = ld_shared_v4(stage_addr + (rl * kStageRow + 4 * cg) * 4);
+        const long long row = row0 + rl;
+        if (row < M && col_ok) epi_vec4(x, row, col, N, ep, bias4, acc_scale, ld[i]);
+      }
     }
   } else {
+    // scalar path (row stride not 16-byte friendly: the fp32 logits).  Lane = column; the column's bias is loaded once.
     const int col = col0 + lane;
+    const bool col_ok = col < N;
+    const bool simple = ep.rowvec == nullptr && ep.mask == nullptr && ep.residual == nullptr && ep.drop.p <= 0.f &&
+                        ep.out_act == nullptr && ep.scale_cols == 0;
+    if (simple) {
+      const float b = (ep.bias != nullptr && col_ok) ? __ldg(ep.bias + col) : 0.f;
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r) {
+        const long long row = row0 + r;
+        float x = ld_shared_f32(stage_addr + (r * kStageRow + lane) * 4) * acc_scale + b;
+        if (ep.relu) x = fmaxf(x, 0.f);
+        if (row < M && col_ok) ep.out_f32[row * (long long)ep.out_f32_ld + col] = x;
+      }
+    } else {
 #pragma unroll 4
-    for (int r = 0; r < 32; ++r) {
-      long long row = row0 + r;
-      float x = ld_shared_f32(stage_addr + (r * kStageRow + lane) * 4);
-      if (row < M && col < N) epi_scalar(x, row, col, N, ep, acc_scale);
+      for (int r = 0; r < 32; ++r) {
+        const long long row = row0 + r;
+        float x = ld_shared_f32(stage_addr + (r * kStageRow + lane) * 4);
+        if (row < M && col_ok) epi_scalar(x, row, col, N, ep, acc_scale);
+      }
     }
   }
   __syncwarp();
