@@ -7,7 +7,7 @@
 //   shapes this kernel does not cover).  tcgen05 is not used here on purpose: a 32 x 32 x 32 problem fills 1/16 of
 //   the smallest UMMA tile (hard part 2); attention is 2.4 % of the step's FLOPs.
 //
-// Dropout on the probabilities uses its own element numbering (8 consecutive Philox words per (row, lane-in-quad)),
+// Dropout on the probabilities uses its own element numbering (8 consecutive draws per (row, lane-in-quad)),
 // identical in forward and backward of THIS kernel.
 #include "../../include/dsvg_b200.h"
 #include "common.cuh"
@@ -121,7 +121,7 @@ __device__ __forceinline__ void softmax_rows(float (&s)[2][4][4], uint32_t key_m
     }
 }
 
-// dropout multipliers in the same layout: 8 consecutive Philox words per (pair, row, t)
+// dropout multipliers in the same layout: 8 consecutive 16-bit draws (4 hashes) per (pair, row, t)
 __device__ __forceinline__ void dropout_tile(float (&mult)[2][4][4], const Dropout& d, unsigned long long pair, int g,
                                              int t) {
 #pragma unroll
@@ -129,13 +129,13 @@ __device__ __forceinline__ void dropout_tile(float (&mult)[2][4][4], const Dropo
 #pragma unroll
     for (int hrow = 0; hrow < 2; ++hrow) {
       const int i = 16 * mt + g + 8 * hrow;
-      const unsigned long long base4 = ((pair * 32 + i) * 4 + t) * 2;  // index of the first group of 4 words
-      uint4 w0 = dropout_words(d, base4), w1 = dropout_words(d, base4 + 1);
-      const uint32_t w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      const unsigned long long base = ((pair * 32 + i) * 4 + t) * 4;  // index of the first pair of draws
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) mult[mt][nt][2 * hrow + e] = w[2 * nt + e] >= d.thr ? d.scale : 0.f;
+      for (int nt = 0; nt < 4; ++nt) {
+        const uint32_t h = dropout_bits(d, base + nt);
+        mult[mt][nt][2 * hrow] = (h & 0xFFFFu) >= d.thr16 ? d.scale : 0.f;
+        mult[mt][nt][2 * hrow + 1] = (h >> 16) >= d.thr16 ? d.scale : 0.f;
+      }
     }
 }
 

@@ -1,5 +1,5 @@
 // Shared device/host helpers: error reporting across the C ABI, the split-bf16 activation format,
-// Philox4x32-10 for in-kernel dropout, warp reductions.
+// the counter-hash dropout generator, warp reductions.
 #pragma once
 #include <cstdint>
 #include <cstdio>
@@ -83,57 +83,54 @@ __device__ __forceinline__ void act_store2(bf16* p, size_t lo_off, size_t i, flo
 }
 
 // ----------------------------------------------------------------------------------------------
-// Philox4x32-10.  A dropout site is (seed, site id); element i of the site's tensor uses word (i & 3) of
-// philox(counter = (i >> 2, site), key = seed).  The backward pass regenerates the same words.
+// Dropout masks: stateless counter-based generator.  A dropout call site is (seed, site id); element i of the site's
+// tensor draws the 16-bit half (i & 1) of  mix32( (i >> 1) * odd ^ key(seed, site) )  and is kept iff draw >= thr16.
+// mix32 is the "lowbias32" integer finaliser (2 multiplies, 3 xor-shifts): ~4 integer ops per element, so that the
+// masks generated inside the GEMM epilogues cost less than the stores they gate (a Philox4x32-10 version measured
+// 2 k instructions per 32x32 chunk and made the epilogue issue-bound).  The backward pass regenerates the same draws.
+// The drop probability is quantised to thr16 / 65536 and the survivors are scaled by its exact complement.
 // ----------------------------------------------------------------------------------------------
 struct Dropout {
-  float p;             // drop probability; 0 disables
-  uint32_t thr;        // keep iff word >= thr   (thr = p * 2^32, host-computed)
-  float scale;         // 1 / (1 - p)
-  uint32_t site;       // call-site id
-  unsigned long long seed;
+  float p;             // requested drop probability; 0 disables
+  uint32_t thr16;      // keep iff 16-bit draw >= thr16
+  float scale;         // 1 / (1 - thr16 / 65536)
+  uint32_t key;        // mixes seed and call-site id (host-computed)
 };
+inline uint32_t host_mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
 inline Dropout make_dropout(float p, uint32_t site, unsigned long long seed) {
   Dropout d;
   d.p = p;
-  double t = double(p) * 4294967296.0;
-  d.thr = t >= 4294967295.0 ? 0xFFFFFFFFu : (t <= 0.0 ? 0u : uint32_t(t));
-  d.scale = p < 1.f ? 1.f / (1.f - p) : 0.f;
-  d.site = site;
-  d.seed = seed;
+  double t = double(p) * 65536.0 + 0.5;
+  d.thr16 = t >= 65535.0 ? 65535u : (t <= 0.0 ? 0u : uint32_t(t));
+  d.scale = 1.f / (1.f - float(d.thr16) / 65536.f);
+  d.key = host_mix32(uint32_t(seed) ^ host_mix32(uint32_t(seed >> 32) + 0x9E3779B9u * (site + 1u)));
   return d;
 }
-
-__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                                               uint32_t k1) {
-  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
-    uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
-    uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
-    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-    k0 += W0; k1 += W1;
-  }
-  return make_uint4(c0, c1, c2, c3);
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
 }
-__device__ __forceinline__ uint4 dropout_words(const Dropout& d, unsigned long long idx4) {
-  return philox4x32_10(uint32_t(idx4), uint32_t(idx4 >> 32), d.site, 0x5eedu, uint32_t(d.seed),
-                       uint32_t(d.seed >> 32));
+// 32 random bits shared by elements 2*pair and 2*pair + 1
+__device__ __forceinline__ uint32_t dropout_bits(const Dropout& d, unsigned long long pair) {
+  return mix32((uint32_t(pair) * 0x9E3779B1u) ^ (uint32_t(pair >> 32) * 0x85EBCA77u) ^ d.key);
 }
-// multiplier (0 or 1/(1-p)) for a single element
+// multiplier (0 or scale) for a single element
 __device__ __forceinline__ float dropout_mult(const Dropout& d, unsigned long long idx) {
   if (d.p <= 0.f) return 1.f;
-  uint4 w = dropout_words(d, idx >> 2);
-  uint32_t r = (idx & 3) == 0 ? w.x : (idx & 3) == 1 ? w.y : (idx & 3) == 2 ? w.z : w.w;
-  return r >= d.thr ? d.scale : 0.f;
+  uint32_t h = dropout_bits(d, idx >> 1);
+  uint32_t draw = (idx & 1) ? (h >> 16) : (h & 0xFFFFu);
+  return draw >= d.thr16 ? d.scale : 0.f;
 }
 // multipliers for 4 consecutive elements starting at idx (idx % 4 == 0)
 __device__ __forceinline__ float4 dropout_mult4(const Dropout& d, unsigned long long idx) {
   if (d.p <= 0.f) return make_float4(1.f, 1.f, 1.f, 1.f);
-  uint4 w = dropout_words(d, idx >> 2);
-  float s = d.scale;
-  return make_float4(w.x >= d.thr ? s : 0.f, w.y >= d.thr ? s : 0.f, w.z >= d.thr ? s : 0.f, w.w >= d.thr ? s : 0.f);
+  const uint32_t h0 = dropout_bits(d, idx >> 1), h1 = dropout_bits(d, (idx >> 1) + 1);
+  const float s = d.scale;
+  return make_float4((h0 & 0xFFFFu) >= d.thr16 ? s : 0.f, (h0 >> 16) >= d.thr16 ? s : 0.f,
+                     (h1 & 0xFFFFu) >= d.thr16 ? s : 0.f, (h1 >> 16) >= d.thr16 ? s : 0.f);
 }
 
 // ----------------------------------------------------------------------------------------------

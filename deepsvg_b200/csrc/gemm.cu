@@ -138,7 +138,8 @@ struct Epi {
   bf16* out_act;
   size_t out_lo_off;
   int out_act_ld;
-  int vec;  // 1: every pointer/stride satisfies the 4-wide vector path
+  int vec;   // 1: every pointer/stride satisfies the 4-wide vector path
+  int mode;  // 0: generic run-time epilogue; k > 0: lean epilogue kLeanFeat[k - 1]
 };
 
 constexpr int kThreads = 192;       // 6 warps
@@ -356,6 +357,121 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&v)[32], uint32_t stage
 }
 
 // ------------------------------------------------------------------------------------------------
+// Lean epilogues.  The generic path above decides every step at run time (~100 instructions per 4 outputs, which made
+// the 8 epilogue warps issue-bound: ncu smsp__issue_active 40 %, 2.4 k instructions per 32x32 chunk).  The model's
+// fast-mode GEMMs use only a handful of step combinations; each is compiled with its steps fixed (FEAT bit mask) and
+// pointer arithmetic hoisted out of the row loop.  All of them require the aligned vector layout (ep.vec != 0) and
+// single-plane act tensors.
+// ------------------------------------------------------------------------------------------------
+enum : uint32_t { F_BIAS = 1, F_SCALE = 2, F_RELU = 4, F_DROP = 8, F_ROWVEC = 16, F_MASK = 32, F_RES = 64,
+                  F_OUTF = 128, F_OUTA = 256, F_ACCS = 512 };
+
+template <uint32_t FEAT>
+__device__ __forceinline__ void epilogue_chunk_lean(uint32_t (&v)[32], uint32_t stage_addr, int lane, int row0, int col0,
+                                                    int M, int N, const Epi& ep) {
+  {
+    const uint32_t my = stage_addr + lane * (kStageRow * 4);
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      st_shared_v4(my + q * 16, __uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                   __uint_as_float(v[4 * q + 3]));
+  }
+  __syncwarp();
+  const int cg = lane & 7, rsub = lane >> 3;
+  const int col = col0 + 4 * cg;
+  if (col < N) {
+    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (FEAT & F_BIAS) bias4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
+    float accs = 1.f;
+    if constexpr (FEAT & F_ACCS) accs = __ldg(ep.acc_scale_dev);
+    const int r_first = row0 + rsub;
+    // row-invariant bases (element offsets); rows advance by 4 per iteration
+    const float* res_p = nullptr;
+    const bf16* mask_p = nullptr;
+    float* outf_p = nullptr;
+    bf16* outa_p = nullptr;
+    if constexpr (FEAT & F_RES) res_p = ep.residual + size_t(r_first) * ep.res_ld + col;
+    if constexpr (FEAT & F_MASK) mask_p = ep.mask + size_t(r_first) * ep.mask_ld + col;
+    if constexpr (FEAT & F_OUTF) outf_p = ep.out_f32 + size_t(r_first) * ep.out_f32_ld + col;
+    if constexpr (FEAT & F_OUTA) outa_p = ep.out_act + size_t(r_first) * ep.out_act_ld + col;
+    const bool has_rv = (FEAT & F_ROWVEC) && ep.rowvec != nullptr;
+    const bool has_drop = (FEAT & F_DROP) && ep.drop.p > 0.f;
+    const uint32_t lds_base = stage_addr + (rsub * kStageRow + 4 * cg) * 4;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float4 res[4];
+      uint2 msk[4];
+      float4 rv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int it = 4 * h + i;
+        const int row = r_first + 4 * it;
+        if (row < M) {
+          if constexpr (FEAT & F_RES) res[i] = *reinterpret_cast<const float4*>(res_p + size_t(4 * it) * ep.res_ld);
+          if constexpr (FEAT & F_MASK) msk[i] = *reinterpret_cast<const uint2*>(mask_p + size_t(4 * it) * ep.mask_ld);
+          if constexpr (FEAT & F_ROWVEC)
+            if (has_rv)
+              rv[i] = __ldg(reinterpret_cast<const float4*>(ep.rowvec + size_t(row / ep.rows_per_group) * ep.rowvec_ld + col));
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int it = 4 * h + i;
+        const int row = r_first + 4 * it;
+        float4 x = ld_shared_v4(lds_base + it * (4 * kStageRow * 4));
+        if (row < M) {
+          if constexpr (FEAT & F_ACCS) { x.x *= accs; x.y *= accs; x.z *= accs; x.w *= accs; }
+          if constexpr (FEAT & F_BIAS) { x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w; }
+          if constexpr (FEAT & F_SCALE) {
+            if (col < ep.scale_cols) { x.x *= ep.scale; x.y *= ep.scale; x.z *= ep.scale; x.w *= ep.scale; }  // scale_cols % 4 == 0
+          }
+          if constexpr (FEAT & F_RELU) {
+            x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
+          }
+          if constexpr (FEAT & F_DROP) {
+            if (has_drop) {
+              float4 m = dropout_mult4(ep.drop, (unsigned long long)row * (unsigned long long)N + col);
+              x.x *= m.x; x.y *= m.y; x.z *= m.z; x.w *= m.w;
+            }
+          }
+          if constexpr (FEAT & F_ROWVEC) {
+            if (has_rv) { x.x += rv[i].x; x.y += rv[i].y; x.z += rv[i].z; x.w += rv[i].w; }
+          }
+          if constexpr (FEAT & F_MASK) {
+            float4 m = bf16x4_to_f4(msk[i]);
+            x.x = m.x != 0.f ? x.x * ep.mask_scale : 0.f;
+            x.y = m.y != 0.f ? x.y * ep.mask_scale : 0.f;
+            x.z = m.z != 0.f ? x.z * ep.mask_scale : 0.f;
+            x.w = m.w != 0.f ? x.w * ep.mask_scale : 0.f;
+          }
+          if constexpr (FEAT & F_RES) { x.x += res[i].x; x.y += res[i].y; x.z += res[i].z; x.w += res[i].w; }
+          if constexpr (FEAT & F_OUTF) *reinterpret_cast<float4*>(outf_p + size_t(4 * it) * ep.out_f32_ld) = x;
+          if constexpr (FEAT & F_OUTA) {
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(x.x, x.y), h1 = __floats2bfloat162_rn(x.z, x.w);
+            uint2 u;
+            u.x = *reinterpret_cast<uint32_t*>(&h0);
+            u.y = *reinterpret_cast<uint32_t*>(&h1);
+            *reinterpret_cast<uint2*>(outa_p + size_t(4 * it) * ep.out_act_ld) = u;
+          }
+        }
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// feature sets with a compiled lean epilogue (index = Epi::mode - 1)
+constexpr uint32_t kLeanFeat[] = {
+    F_OUTA,                                   // 1: plain dgrad
+    F_BIAS | F_SCALE | F_OUTA,                // 2: QKV projection
+    F_BIAS | F_RELU | F_DROP | F_OUTA,        // 3: FFN first linear
+    F_BIAS | F_DROP | F_ROWVEC | F_RES | F_OUTF,  // 4: out-proj / FFN second linear into the fp32 residual stream
+    F_MASK | F_OUTA,                          // 5: dgrad through ReLU (+dropout) mask
+    F_ACCS | F_RES | F_OUTF,                  // 6: head dgrads accumulated in fp32
+};
+constexpr int kNumLean = sizeof(kLeanFeat) / sizeof(kLeanFeat[0]);
+
+// ------------------------------------------------------------------------------------------------
 // dsvg_linear kernel
 // ------------------------------------------------------------------------------------------------
 constexpr int kLinThreads = 320;    // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
@@ -373,7 +489,7 @@ struct LinearCfg {
   static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kStagingBytes + 256;
 };
 
-template <int BN, int NPLANES>
+template <int BN, int NPLANES, int MODE>
 __global__ void __launch_bounds__(kLinThreads, 1)
 linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo, int M, int N, int K,
@@ -512,7 +628,10 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * BN + c), v);
         tmem_ld_wait();
-        epilogue_chunk<false>(v, stage_buf, lane, row0, n0 + c, M, N, ep, 1.f, nullptr, 0);
+        if constexpr (MODE == 0)
+          epilogue_chunk<false>(v, stage_buf, lane, row0, n0 + c, M, N, ep, 1.f, nullptr, 0);
+        else
+          epilogue_chunk_lean<kLeanFeat[MODE - 1]>(v, stage_buf, lane, int(row0), n0 + c, M, N, ep);
       }
       tc_fence_before();
       __syncwarp();
@@ -714,21 +833,58 @@ static int sm_count() {
   return n;
 }
 
-template <int BN, int NPLANES>
-static int launch_linear(const CUtensorMap& a, const CUtensorMap& alo, const CUtensorMap& b, const CUtensorMap& blo,
-                         int M, int N, int K, const Epi& ep, cudaStream_t st) {
+template <int BN, int NPLANES, int MODE>
+static int launch_linear_mode(const CUtensorMap& a, const CUtensorMap& alo, const CUtensorMap& b, const CUtensorMap& blo,
+                              int M, int N, int K, const Epi& ep, cudaStream_t st) {
   using Cfg = LinearCfg<BN, NPLANES>;
   static bool configured = false;
   if (!configured) {
-    DSVG_CUDA(cudaFuncSetAttribute(linear_kernel<BN, NPLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DSVG_CUDA(cudaFuncSetAttribute(linear_kernel<BN, NPLANES, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    Cfg::kSmemBytes));
     configured = true;
   }
   const int tiles = ceil_div(M, kBlockM) * ceil_div(N, BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  linear_kernel<BN, NPLANES><<<grid, kLinThreads, Cfg::kSmemBytes, st>>>(a, alo, b, blo, M, N, K, ep);
+  linear_kernel<BN, NPLANES, MODE><<<grid, kLinThreads, Cfg::kSmemBytes, st>>>(a, alo, b, blo, M, N, K, ep);
   ++g_launches;
   DSVG_LAUNCH_CHECK();
+  return 0;
+}
+template <int BN>
+static int launch_linear_fast(const CUtensorMap& a, const CUtensorMap& b, int M, int N, int K, const Epi& ep,
+                              cudaStream_t st) {
+  switch (ep.mode) {
+    case 1: return launch_linear_mode<BN, 1, 1>(a, a, b, b, M, N, K, ep, st);
+    case 2: return launch_linear_mode<BN, 1, 2>(a, a, b, b, M, N, K, ep, st);
+    case 3: return launch_linear_mode<BN, 1, 3>(a, a, b, b, M, N, K, ep, st);
+    case 4: return launch_linear_mode<BN, 1, 4>(a, a, b, b, M, N, K, ep, st);
+    case 5: return launch_linear_mode<BN, 1, 5>(a, a, b, b, M, N, K, ep, st);
+    case 6: return launch_linear_mode<BN, 1, 6>(a, a, b, b, M, N, K, ep, st);
+    default: return launch_linear_mode<BN, 1, 0>(a, a, b, b, M, N, K, ep, st);
+  }
+}
+
+// which lean epilogue (if any) covers exactly the requested steps
+static int pick_mode(const Epi& ep, bool split) {
+  static const bool off = [] { const char* e = getenv("DSVG_EPI"); return e && e[0] == 'g'; }();  // "generic"
+  if (off || split || ep.vec != 1 || ep.mask_lo_off != 0 || ep.out_lo_off != 0) return 0;
+  uint32_t f = 0;
+  if (ep.acc_scale_dev) f |= F_ACCS;
+  if (ep.bias) f |= F_BIAS;
+  if (ep.scale_cols > 0) f |= F_SCALE;
+  if (ep.relu) f |= F_RELU;
+  if (ep.drop.p > 0.f) f |= F_DROP;
+  if (ep.rowvec) f |= F_ROWVEC;
+  if (ep.mask) f |= F_MASK;
+  if (ep.residual) f |= F_RES;
+  if (ep.out_f32) f |= F_OUTF;
+  if (ep.out_act) f |= F_OUTA;
+  if ((f & F_SCALE) && ep.scale_cols % 4 != 0) return 0;
+  for (int k = 0; k < kNumLean; ++k) {
+    const uint32_t have = kLeanFeat[k];
+    const uint32_t optional = have & (F_DROP | F_ROWVEC);   // run-time checked inside the lean code
+    if ((f & ~optional) == (have & ~optional) && (f & ~have) == 0) return k + 1;
+  }
   return 0;
 }
 
@@ -824,9 +980,9 @@ extern "C" int dsvg_linear(const dsvg_bf16* X, size_t x_lo_off, int lda, const d
     if (make_map(&blo, Wb + w_lo_off, K, N, ldb, 64, bn)) return 1;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (split) return launch_linear<128, 2>(a, alo, b, blo, M, N, K, ep, st);
-  return wide ? launch_linear<256, 1>(a, alo, b, blo, M, N, K, ep, st)
-              : launch_linear<128, 1>(a, alo, b, blo, M, N, K, ep, st);
+  ep.mode = pick_mode(ep, split);
+  if (split) return launch_linear_mode<128, 2, 0>(a, alo, b, blo, M, N, K, ep, st);
+  return wide ? launch_linear_fast<256>(a, b, M, N, K, ep, st) : launch_linear_fast<128>(a, b, M, N, K, ep, st);
 }
 
 extern "C" int dsvg_outer(const dsvg_bf16* A, size_t a_lo_off, int lda, const dsvg_bf16* B, size_t b_lo_off, int ldb,

@@ -11,7 +11,8 @@
  *     (thread-local); no C++ exception crosses this boundary;
  *   - "act" tensors are bf16 with an optional second "lo" plane `lo_off` ELEMENTS after the first
  *     (lo_off = 0: fast single-plane bf16; lo_off != 0: parity mode, value = hi + lo, GEMMs run as bf16x3);
- *   - dropout is Philox4x32-10 keyed by (seed, site); p = 0 disables it (eval mode).
+ *   - dropout masks come from a stateless counter hash keyed by (seed, site, element index); p = 0 disables it
+ *     (eval mode); the backward pass regenerates the forward mask from the same triple.
  */
 #ifndef DSVG_B200_H
 #define DSVG_B200_H

@@ -62,6 +62,50 @@ def test_linear_full_epilogue():
     assert _rel(oa.float(), ref) < 2e-4
 
 
+@pytest.mark.parametrize("mode", ["dgrad", "qkv", "ffn1", "resid", "mask", "head_dgrad"])
+@pytest.mark.parametrize("N", [256, 768, 128])
+def test_linear_lean_epilogues(mode, N):
+    """The compile-time specialised epilogues (one per GEMM role of the model) against the same fp32 restatement."""
+    ops = _ops()
+    M, K, rpg = 1000, 256, 25
+    X, W = _rand(M, K, seed=1), _rand(N, K, seed=2, scale=K ** -0.5)
+    b, res, rv = _rand(N, seed=3), _rand(M, N, seed=4), _rand(M // rpg, N, seed=5)
+    msk = torch.relu(_rand(M, N, seed=6))
+    xa, wa, ma = ops.act_from_float(X, 1), ops.act_from_float(W, 1), ops.act_from_float(msk, 1)
+    acc = xa.float() @ wa.float().t()
+    of, oa = torch.zeros(M, N, device=DEV), ops.Act(M, N, 1, DEV)
+    sc = torch.tensor([0.37], device=DEV)
+    if mode == "dgrad":
+        ops.linear(xa, wa, M, N, K, out_act=oa)
+        ref, got = acc, oa.float()
+    elif mode == "qkv":
+        ops.linear(xa, wa, M, N, K, bias=b, scale_cols=N // 4 * 2, scale=0.25, out_act=oa)
+        ref = acc + b
+        ref[:, :N // 4 * 2] *= 0.25
+        got = oa.float()
+    elif mode == "ffn1":
+        ops.linear(xa, wa, M, N, K, bias=b, relu=True, drop=(0.2, 5, 77), out_act=oa)
+        ka = ops.Act(M, N, 1, DEV)
+        ops.cast_act(torch.ones(M, N, device=DEV), M, N, out=ka, drop=(0.2, 5, 77))
+        ref, got = torch.relu(acc + b) * ka.float(), oa.float()
+    elif mode == "resid":
+        ops.linear(xa, wa, M, N, K, bias=b, drop=(0.2, 6, 77), rowvec=rv, rows_per_group=rpg, residual=res, out_f32=of)
+        ka = ops.Act(M, N, 1, DEV)
+        ops.cast_act(torch.ones(M, N, device=DEV), M, N, out=ka, drop=(0.2, 6, 77))
+        got = of
+        ref = (acc + b) * (ka.float() != 0) / (1 - 13107 / 65536.0) + rv.repeat_interleave(rpg, 0) + res
+    elif mode == "mask":
+        ops.linear(xa, wa, M, N, K, mask=ma, mask_scale=1.25, out_act=oa)
+        ref, got = acc * (ma.float() != 0) * 1.25, oa.float()
+    else:
+        ops.linear(xa, wa, M, N, K, acc_scale=sc, residual=res, out_f32=of)
+        ref, got = acc * 0.37 + res, of
+    tol = 2e-5 if got is of else 6e-3   # bf16 output rounding
+    if mode == "ffn1":
+        ref = torch.relu(acc + b) * (ka.float() != 0) / (1 - 13107 / 65536.0)
+    assert _rel(got, ref) < tol, mode
+
+
 def test_linear_dropout_statistics_and_determinism():
     ops = _ops()
     M, N, K = 1024, 256, 64
