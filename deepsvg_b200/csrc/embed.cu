@@ -70,19 +70,28 @@ seq_prep_kernel(const float* __restrict__ commands, int nseq, int L, int* __rest
 // ---------------------------------------------------------------------------------------------------------
 // fold:  T[k*V + v][c] = sum_e arg_embed[v][e] * W[c][64k + e]
 // ---------------------------------------------------------------------------------------------------------
-__global__ void fold_kernel(const float* __restrict__ Ea, const float* __restrict__ W, float* __restrict__ T, int V,
-                            int n_args, int d) {
+// Block = (argument slot k, chunk of table rows); thread = output channel c, holding its 64 weights in registers.
+__global__ void __launch_bounds__(512)
+fold_kernel(const float* __restrict__ Ea, const float* __restrict__ W, float* __restrict__ T, int V, int n_args, int d,
+            int rows_per_block) {
   __shared__ float ea[64];
-  const int row = blockIdx.x;  // k*V + v
-  const int k = row / V, v = row % V;
-  if (threadIdx.x < 64) ea[threadIdx.x] = Ea[size_t(v) * 64 + threadIdx.x];
-  __syncthreads();
-  for (int c = threadIdx.x; c < d; c += blockDim.x) {
-    const float* w = W + size_t(c) * (64 * n_args) + 64 * k;
+  const int k = blockIdx.y, c = threadIdx.x;
+  float w[64];
+  const float4* wp = reinterpret_cast<const float4*>(W + size_t(c) * (64 * n_args) + 64 * k);
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    float4 t = wp[q];
+    w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
+  }
+  const int v0 = blockIdx.x * rows_per_block, v1 = min(V, v0 + rows_per_block);
+  for (int v = v0; v < v1; ++v) {
+    __syncthreads();
+    if (c < 64) ea[c] = Ea[size_t(v) * 64 + c];
+    __syncthreads();
     float s = 0.f;
-#pragma unroll 16
+#pragma unroll
     for (int e = 0; e < 64; ++e) s = fmaf(ea[e], w[e], s);
-    T[size_t(row) * d + c] = s;
+    T[(size_t(k) * V + v) * d + c] = s;
   }
 }
 // rows v >= 1 become differences to row 0; block (0,0) also writes base = bias + sum_k T[k][0]
@@ -224,27 +233,40 @@ __global__ void unfold_row0_kernel(float* __restrict__ dD, const float* __restri
     if (k == 0) atomicAdd(dbias + c, tot);
   }
 }
-// dEa[v][e] += sum_k sum_c dT[k][v][c] * W[c][64k+e]      (block = v, thread = e)
+// dEa[v][e] += sum_c dT[k][v][c] * W[c][64k+e]      (block = (v, k), thread = e)
 __global__ void unfold_dEa_kernel(const float* __restrict__ dT, const float* __restrict__ W, float* __restrict__ dEa,
                                   int V, int n_args, int d) {
-  const int v = blockIdx.x, e = threadIdx.x;  // 64 threads
-  float s = 0.f;
-  for (int k = 0; k < n_args; ++k) {
-    const float* row = dT + (size_t(k) * V + v) * d;
-    for (int c = 0; c < d; ++c) s = fmaf(row[c], W[size_t(c) * (64 * n_args) + 64 * k + e], s);
+  const int v = blockIdx.x, k = blockIdx.y, e = threadIdx.x;  // 64 threads
+  const float* row = dT + (size_t(k) * V + v) * d;
+  const float* w = W + 64 * k + e;
+  float s0 = 0.f, s1 = 0.f;
+  for (int c = 0; c < d; c += 2) {
+    s0 = fmaf(row[c], w[size_t(c) * (64 * n_args)], s0);
+    s1 = fmaf(row[c + 1], w[size_t(c + 1) * (64 * n_args)], s1);
   }
-  atomicAdd(dEa + size_t(v) * 64 + e, s);
+  atomicAdd(dEa + size_t(v) * 64 + e, s0 + s1);
 }
-// dW[c][64k+e] += sum_v dT[k][v][c] * Ea[v][e]            (block = c, thread = 64k+e)
-__global__ void unfold_dW_kernel(const float* __restrict__ dT, const float* __restrict__ Ea, float* __restrict__ dW,
-                                 int V, int n_args, int d) {
-  const int c = blockIdx.x;
-  for (int j = threadIdx.x; j < 64 * n_args; j += blockDim.x) {
-    const int k = j >> 6, e = j & 63;
-    float s = 0.f;
-    for (int v = 0; v < V; ++v) s = fmaf(dT[(size_t(k) * V + v) * d + c], Ea[size_t(v) * 64 + e], s);
-    atomicAdd(dW + size_t(c) * (64 * n_args) + j, s);
+// dW[c][64k+e] += sum_v dT[k][v][c] * Ea[v][e]   (block = (chunk of v, k), thread = c with 64 register accumulators)
+__global__ void __launch_bounds__(512)
+unfold_dW_kernel(const float* __restrict__ dT, const float* __restrict__ Ea, float* __restrict__ dW, int V, int n_args,
+                 int d, int rows_per_block) {
+  __shared__ float ea[64];
+  const int k = blockIdx.y, c = threadIdx.x;
+  float acc[64];
+#pragma unroll
+  for (int e = 0; e < 64; ++e) acc[e] = 0.f;
+  const int v0 = blockIdx.x * rows_per_block, v1 = min(V, v0 + rows_per_block);
+  for (int v = v0; v < v1; ++v) {
+    __syncthreads();
+    if (c < 64) ea[c] = Ea[size_t(v) * 64 + c];
+    __syncthreads();
+    const float t = dT[(size_t(k) * V + v) * d + c];
+#pragma unroll
+    for (int e = 0; e < 64; ++e) acc[e] = fmaf(t, ea[e], acc[e]);
   }
+  float* out = dW + size_t(c) * (64 * n_args) + 64 * k;
+#pragma unroll
+  for (int e = 0; e < 64; ++e) atomicAdd(out + e, acc[e]);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -303,7 +325,11 @@ extern "C" int dsvg_embed_fold(const float* arg_embed, const float* W, const flo
                                int V, int n_args, int d, void* stream) {
   DSVG_CHECK(arg_embed && W && bias && table && base, "dsvg_embed_fold: null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  fold_kernel<<<n_args * V, 256, 0, st>>>(arg_embed, W, table, V, n_args, d);
+  DSVG_CHECK(d <= 512 && d >= 64, "dsvg_embed_fold: d_model must be in [64, 512]");
+  {
+    const int rpb = 16;
+    fold_kernel<<<dim3(ceil_div(V, rpb), n_args), d, 0, st>>>(arg_embed, W, table, V, n_args, d, rpb);
+  }
   ++g_launches;
   DSVG_LAUNCH_CHECK();
   fold_sub_kernel<<<dim3(16, n_args), 256, 0, st>>>(table, bias, base, V, n_args, d);
@@ -358,10 +384,10 @@ extern "C" int dsvg_embed_bwd(const float* commands, const float* args, const ui
   unfold_row0_kernel<<<n_args, 256, 0, st>>>(scratch_table, d_pos_tab, d_bias, V, L, d);
   ++g_launches;
   DSVG_LAUNCH_CHECK();
-  unfold_dEa_kernel<<<V, 64, 0, st>>>(scratch_table, W, d_arg_embed, V, n_args, d);
+  unfold_dEa_kernel<<<dim3(V, n_args), 64, 0, st>>>(scratch_table, W, d_arg_embed, V, n_args, d);
   ++g_launches;
   DSVG_LAUNCH_CHECK();
-  unfold_dW_kernel<<<d, 256, 0, st>>>(scratch_table, arg_embed, d_W, V, n_args, d);
+  unfold_dW_kernel<<<dim3(ceil_div(V, 32), n_args), d, 0, st>>>(scratch_table, arg_embed, d_W, V, n_args, d, 32);
   ++g_launches;
   DSVG_LAUNCH_CHECK();
   return 0;

@@ -366,9 +366,33 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&v)[32], uint32_t stage
 enum : uint32_t { F_BIAS = 1, F_SCALE = 2, F_RELU = 4, F_DROP = 8, F_ROWVEC = 16, F_MASK = 32, F_RES = 64,
                   F_OUTF = 128, F_OUTA = 256, F_ACCS = 512 };
 
+// global-memory operands of one 32x32 chunk (8 row-iterations of this lane), fetched one chunk ahead of their use
+template <uint32_t FEAT>
+struct LeanPre {
+  float4 res[(FEAT & F_RES) ? 8 : 1];
+  uint2 msk[(FEAT & F_MASK) ? 8 : 1];
+};
+template <uint32_t FEAT>
+__device__ __forceinline__ void lean_prefetch(LeanPre<FEAT>& p, int lane, int row0, int col0, int M, int N, const Epi& ep) {
+  if constexpr ((FEAT & (F_RES | F_MASK)) != 0) {
+    const int cg = lane & 7, rsub = lane >> 3;
+    const int col = col0 + 4 * cg;
+    if (col < N) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int row = row0 + rsub + 4 * it;
+        if (row < M) {
+          if constexpr (FEAT & F_RES) p.res[it] = *reinterpret_cast<const float4*>(ep.residual + size_t(row) * ep.res_ld + col);
+          if constexpr (FEAT & F_MASK) p.msk[it] = *reinterpret_cast<const uint2*>(ep.mask + size_t(row) * ep.mask_ld + col);
+        }
+      }
+    }
+  }
+}
+
 template <uint32_t FEAT>
 __device__ __forceinline__ void epilogue_chunk_lean(uint32_t (&v)[32], uint32_t stage_addr, int lane, int row0, int col0,
-                                                    int M, int N, const Epi& ep) {
+                                                    int M, int N, const Epi& ep, const LeanPre<FEAT>& pre) {
   {
     const uint32_t my = stage_addr + lane * (kStageRow * 4);
 #pragma unroll
@@ -385,74 +409,55 @@ __device__ __forceinline__ void epilogue_chunk_lean(uint32_t (&v)[32], uint32_t 
     float accs = 1.f;
     if constexpr (FEAT & F_ACCS) accs = __ldg(ep.acc_scale_dev);
     const int r_first = row0 + rsub;
-    // row-invariant bases (element offsets); rows advance by 4 per iteration
-    const float* res_p = nullptr;
-    const bf16* mask_p = nullptr;
     float* outf_p = nullptr;
     bf16* outa_p = nullptr;
-    if constexpr (FEAT & F_RES) res_p = ep.residual + size_t(r_first) * ep.res_ld + col;
-    if constexpr (FEAT & F_MASK) mask_p = ep.mask + size_t(r_first) * ep.mask_ld + col;
     if constexpr (FEAT & F_OUTF) outf_p = ep.out_f32 + size_t(r_first) * ep.out_f32_ld + col;
     if constexpr (FEAT & F_OUTA) outa_p = ep.out_act + size_t(r_first) * ep.out_act_ld + col;
     const bool has_rv = (FEAT & F_ROWVEC) && ep.rowvec != nullptr;
     const bool has_drop = (FEAT & F_DROP) && ep.drop.p > 0.f;
     const uint32_t lds_base = stage_addr + (rsub * kStageRow + 4 * cg) * 4;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      float4 res[4];
-      uint2 msk[4];
-      float4 rv[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int it = 4 * h + i;
-        const int row = r_first + 4 * it;
-        if (row < M) {
-          if constexpr (FEAT & F_RES) res[i] = *reinterpret_cast<const float4*>(res_p + size_t(4 * it) * ep.res_ld);
-          if constexpr (FEAT & F_MASK) msk[i] = *reinterpret_cast<const uint2*>(mask_p + size_t(4 * it) * ep.mask_ld);
-          if constexpr (FEAT & F_ROWVEC)
-            if (has_rv)
-              rv[i] = __ldg(reinterpret_cast<const float4*>(ep.rowvec + size_t(row / ep.rows_per_group) * ep.rowvec_ld + col));
+    for (int it = 0; it < 8; ++it) {
+      const int row = r_first + 4 * it;
+      float4 x = ld_shared_v4(lds_base + it * (4 * kStageRow * 4));
+      if (row < M) {
+        if constexpr (FEAT & F_ACCS) { x.x *= accs; x.y *= accs; x.z *= accs; x.w *= accs; }
+        if constexpr (FEAT & F_BIAS) { x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w; }
+        if constexpr (FEAT & F_SCALE) {
+          if (col < ep.scale_cols) { x.x *= ep.scale; x.y *= ep.scale; x.z *= ep.scale; x.w *= ep.scale; }  // scale_cols % 4 == 0
         }
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int it = 4 * h + i;
-        const int row = r_first + 4 * it;
-        float4 x = ld_shared_v4(lds_base + it * (4 * kStageRow * 4));
-        if (row < M) {
-          if constexpr (FEAT & F_ACCS) { x.x *= accs; x.y *= accs; x.z *= accs; x.w *= accs; }
-          if constexpr (FEAT & F_BIAS) { x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w; }
-          if constexpr (FEAT & F_SCALE) {
-            if (col < ep.scale_cols) { x.x *= ep.scale; x.y *= ep.scale; x.z *= ep.scale; x.w *= ep.scale; }  // scale_cols % 4 == 0
+        if constexpr (FEAT & F_RELU) {
+          x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
+        }
+        if constexpr (FEAT & F_DROP) {
+          if (has_drop) {
+            float4 m = dropout_mult4(ep.drop, (unsigned long long)row * (unsigned long long)N + col);
+            x.x *= m.x; x.y *= m.y; x.z *= m.z; x.w *= m.w;
           }
-          if constexpr (FEAT & F_RELU) {
-            x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
+        }
+        if constexpr (FEAT & F_ROWVEC) {
+          if (has_rv) {
+            float4 rv = __ldg(reinterpret_cast<const float4*>(ep.rowvec + size_t(row / ep.rows_per_group) * ep.rowvec_ld + col));
+            x.x += rv.x; x.y += rv.y; x.z += rv.z; x.w += rv.w;
           }
-          if constexpr (FEAT & F_DROP) {
-            if (has_drop) {
-              float4 m = dropout_mult4(ep.drop, (unsigned long long)row * (unsigned long long)N + col);
-              x.x *= m.x; x.y *= m.y; x.z *= m.z; x.w *= m.w;
-            }
-          }
-          if constexpr (FEAT & F_ROWVEC) {
-            if (has_rv) { x.x += rv[i].x; x.y += rv[i].y; x.z += rv[i].z; x.w += rv[i].w; }
-          }
-          if constexpr (FEAT & F_MASK) {
-            float4 m = bf16x4_to_f4(msk[i]);
-            x.x = m.x != 0.f ? x.x * ep.mask_scale : 0.f;
-            x.y = m.y != 0.f ? x.y * ep.mask_scale : 0.f;
-            x.z = m.z != 0.f ? x.z * ep.mask_scale : 0.f;
-            x.w = m.w != 0.f ? x.w * ep.mask_scale : 0.f;
-          }
-          if constexpr (FEAT & F_RES) { x.x += res[i].x; x.y += res[i].y; x.z += res[i].z; x.w += res[i].w; }
-          if constexpr (FEAT & F_OUTF) *reinterpret_cast<float4*>(outf_p + size_t(4 * it) * ep.out_f32_ld) = x;
-          if constexpr (FEAT & F_OUTA) {
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(x.x, x.y), h1 = __floats2bfloat162_rn(x.z, x.w);
-            uint2 u;
-            u.x = *reinterpret_cast<uint32_t*>(&h0);
-            u.y = *reinterpret_cast<uint32_t*>(&h1);
-            *reinterpret_cast<uint2*>(outa_p + size_t(4 * it) * ep.out_act_ld) = u;
-          }
+        }
+        if constexpr (FEAT & F_MASK) {
+          float4 m = bf16x4_to_f4(pre.msk[it]);
+          x.x = m.x != 0.f ? x.x * ep.mask_scale : 0.f;
+          x.y = m.y != 0.f ? x.y * ep.mask_scale : 0.f;
+          x.z = m.z != 0.f ? x.z * ep.mask_scale : 0.f;
+          x.w = m.w != 0.f ? x.w * ep.mask_scale : 0.f;
+        }
+        if constexpr (FEAT & F_RES) {
+          x.x += pre.res[it].x; x.y += pre.res[it].y; x.z += pre.res[it].z; x.w += pre.res[it].w;
+        }
+        if constexpr (FEAT & F_OUTF) *reinterpret_cast<float4*>(outf_p + size_t(4 * it) * ep.out_f32_ld) = x;
+        if constexpr (FEAT & F_OUTA) {
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(x.x, x.y), h1 = __floats2bfloat162_rn(x.z, x.w);
+          uint2 u;
+          u.x = *reinterpret_cast<uint32_t*>(&h0);
+          u.y = *reinterpret_cast<uint32_t*>(&h1);
+          *reinterpret_cast<uint2*>(outa_p + size_t(4 * it) * ep.out_act_ld) = u;
         }
       }
     }
@@ -619,19 +624,37 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       const uint32_t acc_phase = (it >> 1) & 1;
       const int m0 = (tile / n_tiles) * kBlockM;
       const int n0 = (tile % n_tiles) * BN;
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
       const long long row0 = (long long)m0 + quarter * 32;
+      if constexpr (MODE == 0) {
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
 #pragma unroll 1
-      for (int c = half * 32; c < BN; c += 64) {
-        if (n0 + c >= N) break;
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * BN + c), v);
-        tmem_ld_wait();
-        if constexpr (MODE == 0)
+        for (int c = half * 32; c < BN; c += 64) {
+          if (n0 + c >= N) break;
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * BN + c), v);
+          tmem_ld_wait();
           epilogue_chunk<false>(v, stage_buf, lane, row0, n0 + c, M, N, ep, 1.f, nullptr, 0);
-        else
-          epilogue_chunk_lean<kLeanFeat[MODE - 1]>(v, stage_buf, lane, int(row0), n0 + c, M, N, ep);
+        }
+      } else {
+        constexpr uint32_t FEAT = kLeanFeat[MODE > 0 ? MODE - 1 : 0];
+        // residual / mask operands are fetched one chunk ahead: the first chunk's loads fly while the MMAs of this
+        // tile are still running, the others while the previous chunk is being written out
+        LeanPre<FEAT> pre[2];
+        lean_prefetch<FEAT>(pre[0], lane, int(row0), n0 + half * 32, M, N, ep);
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll
+        for (int ci = 0; ci < BN / 64; ++ci) {
+          const int c = half * 32 + 64 * ci;
+          if (n0 + c < N) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * BN + c), v);
+            if (ci + 1 < BN / 64) lean_prefetch<FEAT>(pre[(ci + 1) & 1], lane, int(row0), n0 + c + 64, M, N, ep);
+            tmem_ld_wait();
+            epilogue_chunk_lean<FEAT>(v, stage_buf, lane, int(row0), n0 + c, M, N, ep, pre[ci & 1]);
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -901,7 +924,7 @@ static int launch_outer(const CUtensorMap& a, const CUtensorMap& alo, const CUte
   }
   const int out_tiles = ceil_div(P, 128) * ceil_div(Q, BQ);
   const int total_mblk = ceil_div(M, 64);
-  int splits = (2 * sm_count() + out_tiles - 1) / out_tiles;  // ~2 CTAs per SM in flight over the launch
+  int splits = sm_count() / out_tiles;  // one CTA per SM fits (shared memory): fill exactly one wave, no ragged tail
   if (splits > total_mblk / 4) splits = total_mblk / 4;       // keep >= 4 blocks of 64 rows per split
   if (splits < 1) splits = 1;
   const int per = ceil_div(total_mblk, splits);
