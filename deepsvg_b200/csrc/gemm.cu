@@ -477,17 +477,100 @@ constexpr uint32_t kLeanFeat[] = {
 constexpr int kNumLean = sizeof(kLeanFeat) / sizeof(kLeanFeat[0]);
 
 // ------------------------------------------------------------------------------------------------
+// TMA-store epilogue (act outputs): thread = accumulator row, 32 columns straight from TMEM; every step runs in
+// registers, the bf16 result goes into a 128-byte-swizzled [128 x BN] tile in shared memory and leaves the SM as one
+// bulk tensor store per 64-column box.  No shared-memory read-back, no per-thread global stores.
+// ------------------------------------------------------------------------------------------------
+template <uint32_t FEAT>
+__device__ __forceinline__ void tma_out_chunk(uint32_t (&v)[32], uint8_t* out_tile, int r, long long grow, int gc0, int c,
+                                              int M, int N, const Epi& ep, const uint4 (&mk)[4]) {
+  float x[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+  if constexpr (FEAT & F_BIAS) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if (gc0 + 4 * q < N) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + gc0 + 4 * q));
+        x[4 * q] += b.x; x[4 * q + 1] += b.y; x[4 * q + 2] += b.z; x[4 * q + 3] += b.w;
+      }
+    }
+  }
+  if constexpr (FEAT & F_SCALE) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (gc0 + j < ep.scale_cols) x[j] *= ep.scale;
+  }
+  if constexpr (FEAT & F_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+  }
+  if constexpr (FEAT & F_DROP) {
+    if (ep.drop.p > 0.f) {
+      const unsigned long long base = (unsigned long long)grow * (unsigned long long)N + (unsigned long long)gc0;  // even
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const uint32_t h = dropout_bits(ep.drop, (base >> 1) + q);
+        x[2 * q] *= (h & 0xFFFFu) >= ep.drop.thr16 ? ep.drop.scale : 0.f;
+        x[2 * q + 1] *= (h >> 16) >= ep.drop.thr16 ? ep.drop.scale : 0.f;
+      }
+    }
+  }
+  if constexpr (FEAT & F_MASK) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t w[4] = {mk[q].x, mk[q].y, mk[q].z, mk[q].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        // a bf16 is non-zero iff any of its 15 magnitude bits is set
+        x[8 * q + 2 * e] = (w[e] & 0x7FFFu) ? x[8 * q + 2 * e] * ep.mask_scale : 0.f;
+        x[8 * q + 2 * e + 1] = (w[e] & 0x7FFF0000u) ? x[8 * q + 2 * e + 1] * ep.mask_scale : 0.f;
+      }
+    }
+  }
+  // pack and store: 4 x 16 bytes at swizzled positions of row r in the 64-column box (c / 64)
+  uint8_t* box = out_tile + (c >> 6) * (kBlockM * 128) + r * 128;
+  const int j0 = (c & 63) >> 3;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 u;
+    __nv_bfloat162 t;
+    t = __floats2bfloat162_rn(x[8 * q], x[8 * q + 1]); u.x = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(x[8 * q + 2], x[8 * q + 3]); u.y = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(x[8 * q + 4], x[8 * q + 5]); u.z = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(x[8 * q + 6], x[8 * q + 7]); u.w = *reinterpret_cast<uint32_t*>(&t);
+    *reinterpret_cast<uint4*>(box + (((j0 + q) ^ (r & 7)) << 4)) = u;
+  }
+}
+template <uint32_t FEAT>
+__device__ __forceinline__ void tma_out_load_mask(uint4 (&mk)[4], long long grow, int gc0, int M, int N, const Epi& ep) {
+  if constexpr (FEAT & F_MASK) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      mk[q] = make_uint4(0, 0, 0, 0);
+      if (grow < M && gc0 + 8 * q < N)
+        mk[q] = *reinterpret_cast<const uint4*>(ep.mask + size_t(grow) * ep.mask_ld + gc0 + 8 * q);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // dsvg_linear kernel
 // ------------------------------------------------------------------------------------------------
-constexpr int kLinThreads = 320;    // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
-constexpr int kLinEpiWarps = 8;
+// warp 0 TMA, warp 1 MMA, then E epilogue warps (E/4 per TMEM lane quarter).  The store-only lean epilogues (modes 1-3)
+// are latency-bound on the TMEM -> smem -> global chain and need few registers, so they run 16 warps; the others 8.
+__host__ __device__ constexpr int lin_epi_warps(int mode, int bn) { return 8; }
+// act-output lean modes write their bf16 tile through shared memory with one TMA store per 64-column box
+__host__ __device__ constexpr bool lin_tma_out(int mode) { return mode == 1 || mode == 2 || mode == 3 || mode == 5; }
 
-template <int BN, int NPLANES>
+template <int BN, int NPLANES, int MODE = 0>
 struct LinearCfg {
+  static constexpr int kEpiWarps = lin_epi_warps(MODE, BN);
+  static constexpr int kThreads = 64 + 32 * kEpiWarps;
   static constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB
   static constexpr int kBBytes = BN * kBlockK * 2;       // 16/32 KB
   static constexpr int kStageBytes = NPLANES * (kABytes + kBBytes);
-  static constexpr int kStagingBytes = kLinEpiWarps * kStageWarpBytes;
+  static constexpr int kStagingBytes = lin_tma_out(MODE) ? BN * kBlockM * 2 : kEpiWarps * kStageWarpBytes;
   static constexpr int kStages = (212 * 1024 - kStagingBytes) / kStageBytes > 4 ? 4 : (212 * 1024 - kStagingBytes) / kStageBytes;
   static_assert(kStages >= 2, "linear: at least two pipeline stages must fit");
   static constexpr int kTmemCols = 2 * BN;  // two accumulator stages (256 or 512: powers of two)
@@ -495,11 +578,12 @@ struct LinearCfg {
 };
 
 template <int BN, int NPLANES, int MODE>
-__global__ void __launch_bounds__(kLinThreads, 1)
+__global__ void __launch_bounds__((LinearCfg<BN, NPLANES, MODE>::kThreads), 1)
 linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
-              const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo, int M, int N, int K,
-              Epi ep) {
-  using Cfg = LinearCfg<BN, NPLANES>;
+              const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
+              const __grid_constant__ CUtensorMap tmC, int M, int N, int K, Epi ep) {
+  using Cfg = LinearCfg<BN, NPLANES, MODE>;
+  constexpr int kCols = Cfg::kEpiWarps * 8;   // accumulator columns drained per pass of all epilogue warps (64 or 128)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* tiles = smem;
@@ -527,7 +611,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], kLinEpiWarps);
+      mbar_init(&tempty_bar[a], Cfg::kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -616,7 +700,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   } else {
     // =================== epilogue warps (2..9) ===================
     const int quarter = warp & 3;         // TMEM lane quarter this warp may read
-    const int half = (warp - 2) >> 2;     // which of the two column-chunk parities this warp drains
+    const int half = (warp - 2) >> 2;     // which 32-column chunk of every kCols-wide pass this warp drains
     const uint32_t stage_buf = smem_u32(staging) + (warp - 2) * kStageWarpBytes;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -629,13 +713,48 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
 #pragma unroll 1
-        for (int c = half * 32; c < BN; c += 64) {
+        for (int c = half * 32; c < BN; c += kCols) {
           if (n0 + c >= N) break;
           uint32_t v[32];
           tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * BN + c), v);
           tmem_ld_wait();
           epilogue_chunk<false>(v, stage_buf, lane, row0, n0 + c, M, N, ep, 1.f, nullptr, 0);
         }
+      } else if constexpr (lin_tma_out(MODE)) {
+        constexpr uint32_t FEAT = kLeanFeat[MODE > 0 ? MODE - 1 : 0];
+        uint8_t* out_tile = reinterpret_cast<uint8_t*>(staging);
+        const int r = quarter * 32 + lane;
+        const long long grow = (long long)m0 + r;
+        uint4 mk[2][4];
+        tma_out_load_mask<FEAT>(mk[0], grow, n0 + half * 32, M, N, ep);
+        // the previous tile's bulk stores must have finished reading the staging tile before it is overwritten
+        if (warp == 2 && lane == 0) tma_store_wait_read();
+        named_bar_sync(1, Cfg::kEpiWarps * 32);
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll
+        for (int ci = 0; ci < BN / kCols; ++ci) {
+          const int c = half * 32 + kCols * ci;
+          if (n0 + c < N) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * BN + c), v);
+            if (ci + 1 < BN / kCols) tma_out_load_mask<FEAT>(mk[(ci + 1) & 1], grow, n0 + c + kCols, M, N, ep);
+            tmem_ld_wait();
+            tma_out_chunk<FEAT>(v, out_tile, r, grow, n0 + c, c, M, N, ep, mk[ci & 1]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);     // TMEM stage drained: the MMA warp may start tile it + 2
+        fence_proxy_async_smem();                          // generic-proxy smem writes -> visible to the TMA engine
+        named_bar_sync(1, Cfg::kEpiWarps * 32);
+        if (warp == 2 && lane == 0) {
+#pragma unroll
+          for (int bx = 0; bx < BN / 64; ++bx)
+            if (n0 + 64 * bx < N) tma_store_2d(&tmC, out_tile + bx * (kBlockM * 128), n0 + 64 * bx, m0);
+          tma_store_commit();
+        }
+        continue;
       } else {
         constexpr uint32_t FEAT = kLeanFeat[MODE > 0 ? MODE - 1 : 0];
         // residual / mask operands are fetched one chunk ahead: the first chunk's loads fly while the MMAs of this
@@ -645,12 +764,12 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
 #pragma unroll
-        for (int ci = 0; ci < BN / 64; ++ci) {
-          const int c = half * 32 + 64 * ci;
+        for (int ci = 0; ci < BN / kCols; ++ci) {
+          const int c = half * 32 + kCols * ci;
           if (n0 + c < N) {
             uint32_t v[32];
             tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * BN + c), v);
-            if (ci + 1 < BN / 64) lean_prefetch<FEAT>(pre[(ci + 1) & 1], lane, int(row0), n0 + c + 64, M, N, ep);
+            if (ci + 1 < BN / kCols) lean_prefetch<FEAT>(pre[(ci + 1) & 1], lane, int(row0), n0 + c + kCols, M, N, ep);
             tmem_ld_wait();
             epilogue_chunk_lean<FEAT>(v, stage_buf, lane, int(row0), n0 + c, M, N, ep, pre[ci & 1]);
           }
@@ -659,6 +778,9 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+    if constexpr (lin_tma_out(MODE)) {
+      if (warp == 2 && lane == 0) tma_store_wait_all();   // bulk stores must complete before the CTA's smem goes away
     }
   }
 
@@ -859,7 +981,11 @@ static int sm_count() {
 template <int BN, int NPLANES, int MODE>
 static int launch_linear_mode(const CUtensorMap& a, const CUtensorMap& alo, const CUtensorMap& b, const CUtensorMap& blo,
                               int M, int N, int K, const Epi& ep, cudaStream_t st) {
-  using Cfg = LinearCfg<BN, NPLANES>;
+  CUtensorMap c = a;
+  if (lin_tma_out(MODE)) {
+    if (make_map(&c, ep.out_act, N, M, ep.out_act_ld, 64, 128)) return 1;
+  }
+  using Cfg = LinearCfg<BN, NPLANES, MODE>;
   static bool configured = false;
   if (!configured) {
     DSVG_CUDA(cudaFuncSetAttribute(linear_kernel<BN, NPLANES, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -868,7 +994,7 @@ static int launch_linear_mode(const CUtensorMap& a, const CUtensorMap& alo, cons
   }
   const int tiles = ceil_div(M, kBlockM) * ceil_div(N, BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  linear_kernel<BN, NPLANES, MODE><<<grid, kLinThreads, Cfg::kSmemBytes, st>>>(a, alo, b, blo, M, N, K, ep);
+  linear_kernel<BN, NPLANES, MODE><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(a, alo, b, blo, c, M, N, K, ep);
   ++g_launches;
   DSVG_LAUNCH_CHECK();
   return 0;
@@ -888,7 +1014,7 @@ static int launch_linear_fast(const CUtensorMap& a, const CUtensorMap& b, int M,
 }
 
 // which lean epilogue (if any) covers exactly the requested steps
-static int pick_mode(const Epi& ep, bool split) {
+static int pick_mode(const Epi& ep, bool split, int N) {
   static const bool off = [] { const char* e = getenv("DSVG_EPI"); return e && e[0] == 'g'; }();  // "generic"
   if (off || split || ep.vec != 1 || ep.mask_lo_off != 0 || ep.out_lo_off != 0) return 0;
   uint32_t f = 0;
@@ -906,7 +1032,15 @@ static int pick_mode(const Epi& ep, bool split) {
   for (int k = 0; k < kNumLean; ++k) {
     const uint32_t have = kLeanFeat[k];
     const uint32_t optional = have & (F_DROP | F_ROWVEC);   // run-time checked inside the lean code
-    if ((f & ~optional) == (have & ~optional) && (f & ~have) == 0) return k + 1;
+    if ((f & ~optional) == (have & ~optional) && (f & ~have) == 0) {
+      if (lin_tma_out(k + 1)) {
+        const bool ok = N % 8 == 0 && ep.out_act_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(ep.out_act) & 15) == 0 &&
+                        (!ep.mask || (ep.mask_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(ep.mask) & 15) == 0)) &&
+                        (!ep.bias || (reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0);
+        if (!ok) return 0;
+      }
+      return k + 1;
+    }
   }
   return 0;
 }
@@ -1003,7 +1137,7 @@ extern "C" int dsvg_linear(const dsvg_bf16* X, size_t x_lo_off, int lda, const d
     if (make_map(&blo, Wb + w_lo_off, K, N, ldb, 64, bn)) return 1;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  ep.mode = pick_mode(ep, split);
+  ep.mode = pick_mode(ep, split, N);
   if (split) return launch_linear_mode<128, 2, 0>(a, alo, b, blo, M, N, K, ep, st);
   return wide ? launch_linear_fast<256>(a, b, M, N, K, ep, st) : launch_linear_fast<128>(a, b, M, N, K, ep, st);
 }
