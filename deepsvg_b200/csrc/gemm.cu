@@ -127,6 +127,7 @@ struct Epi {
   const float* rowvec;
   int rowvec_ld;
   int rows_per_group;
+  uint32_t rpg_magic;  // ceil(2^32 / rows_per_group): row / rows_per_group == __umulhi(row, magic) while row * rpg < 2^32
   const bf16* mask;
   size_t mask_lo_off;
   int mask_ld;
@@ -437,7 +438,8 @@ __device__ __forceinline__ void epilogue_chunk_lean(uint32_t (&v)[32], uint32_t 
         }
         if constexpr (FEAT & F_ROWVEC) {
           if (has_rv) {
-            float4 rv = __ldg(reinterpret_cast<const float4*>(ep.rowvec + size_t(row / ep.rows_per_group) * ep.rowvec_ld + col));
+            const uint32_t grp = ep.rpg_magic ? __umulhi(uint32_t(row), ep.rpg_magic) : uint32_t(row / ep.rows_per_group);
+            float4 rv = __ldg(reinterpret_cast<const float4*>(ep.rowvec + size_t(grp) * ep.rowvec_ld + col));
             x.x += rv.x; x.y += rv.y; x.z += rv.z; x.w += rv.w;
           }
         }
@@ -1100,6 +1102,9 @@ extern "C" int dsvg_linear(const dsvg_bf16* X, size_t x_lo_off, int lda, const d
   ep.rowvec = e->rowvec;
   ep.rowvec_ld = e->rowvec_ld;
   ep.rows_per_group = e->rows_per_group > 0 ? e->rows_per_group : 1;
+  ep.rpg_magic = 0;
+  if (ep.rows_per_group > 1 && (unsigned long long)M * ep.rows_per_group < (1ull << 32))
+    ep.rpg_magic = uint32_t(((1ull << 32) + ep.rows_per_group - 1) / ep.rows_per_group);
   ep.mask = reinterpret_cast<const bf16*>(e->mask);
   ep.mask_lo_off = e->mask_lo_off;
   ep.mask_ld = e->mask_ld;
