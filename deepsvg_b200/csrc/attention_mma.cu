@@ -259,6 +259,8 @@ __device__ __forceinline__ void store_c_smem(bf16* tile, const float (&c)[2][4][
 constexpr int kMmaWarps = 4;
 
 __global__ void __launch_bounds__(kMmaWarps * 32) attn_mma_fwd_kernel(MmaAttnArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ __align__(16) bf16 sm[kMmaWarps][3 * kTile];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int L = a.L, d = a.H * 32, ld = 3 * d;
@@ -297,6 +299,8 @@ __global__ void __launch_bounds__(kMmaWarps * 32) attn_mma_fwd_kernel(MmaAttnArg
 }
 
 __global__ void __launch_bounds__(kMmaWarps * 32) attn_mma_bwd_kernel(MmaAttnArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(16) bf16 sm_dyn[];   // kMmaWarps x 6 tiles (60 KB: above the static limit)
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int L = a.L, d = a.H * 32, ld = 3 * d;
@@ -381,9 +385,8 @@ int dsvg_attn_mma_fwd(const bf16* qkv, const uint8_t* valid, bf16* out, int nseq
   a.qkv = qkv; a.valid = valid; a.out = out; a.nseq = nseq; a.L = L; a.H = H; a.scale = 1.f; a.drop = drop;
   long long blocks = ((long long)nseq * H + kMmaWarps - 1) / kMmaWarps;
   if (blocks > 148LL * 32) blocks = 148LL * 32;
-  attn_mma_fwd_kernel<<<int(blocks), kMmaWarps * 32, 0, st>>>(a);
+  DSVG_CUDA(launch_k(attn_mma_fwd_kernel, dim3(int(blocks)), dim3(kMmaWarps * 32), 0, st, a));
   ++g_launches;
-  DSVG_LAUNCH_CHECK();
   return 0;
 }
 int dsvg_attn_mma_bwd(const bf16* qkv, const uint8_t* valid, const bf16* dout, bf16* dqkv, int nseq, int L, int H,
@@ -399,8 +402,7 @@ int dsvg_attn_mma_bwd(const bf16* qkv, const uint8_t* valid, const bf16* dout, b
     DSVG_CUDA(cudaFuncSetAttribute(attn_mma_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  attn_mma_bwd_kernel<<<int(blocks), kMmaWarps * 32, smem, st>>>(a);
+  DSVG_CUDA(launch_k(attn_mma_bwd_kernel, dim3(int(blocks)), dim3(kMmaWarps * 32), size_t(smem), st, a));
   ++g_launches;
-  DSVG_LAUNCH_CHECK();
   return 0;
 }

@@ -149,4 +149,31 @@ __device__ __forceinline__ float warp_max(float v) {
 
 inline int ceil_div(long long a, long long b) { return int((a + b - 1) / b); }
 
+// ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  Kernels launched through launch_k() may start while their predecessor in the stream
+// is still draining: they run their prologue (barrier init, TMEM allocation, descriptor prefetch ...) and then block in
+// pdl_wait() until the predecessor has completed and its memory is visible.  EVERY kernel launched with launch_k() must
+// call pdl_wait() before its first access to global memory.  ~400 dependent launches per train step: this hides the
+// launch gap and the prologues of the many small group-level kernels.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(static_cast<Args&&>(args))...);
+}
+
 }  // namespace dsvg

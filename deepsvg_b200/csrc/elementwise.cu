@@ -13,6 +13,8 @@ __global__ void __launch_bounds__(256)
 cast_act_kernel(const float* __restrict__ in, int ld_in, int R, int C, bf16* __restrict__ out, size_t out_lo, int ld_out,
                 bf16* __restrict__ outT, size_t outT_lo, int ld_t, const bf16* __restrict__ mask, size_t mask_lo,
                 int ld_mask, float mask_scale, Dropout drop) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 rows per pass
@@ -53,6 +55,8 @@ colsum_kernel(const bf16* __restrict__ a, size_t lo, int ld, int M, int N, int r
 __global__ void __launch_bounds__(256)
 seg_sum_kernel(const float* __restrict__ in, int nseq, int L, int d, bf16* __restrict__ out, size_t out_lo,
                float* __restrict__ out_f32, Dropout drop) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t n = size_t(nseq) * d;
   for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
     const size_t q = i / d, c = i % d;
@@ -78,6 +82,8 @@ __global__ void scatter_rows_kernel(const float* __restrict__ g, const long long
 
 // y = a + b (fp32), used to merge gradient streams of the tiny latent path
 __global__ void add_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y, size_t n) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
     y[i] = a[i] + b[i];
 }
@@ -94,12 +100,11 @@ extern "C" int dsvg_cast_act(const float* in, int ld_in, int R, int C, dsvg_bf16
   const int cols = out ? (ld_out > C ? ld_out : C) : C;
   const int rows = outT ? (ld_t > R ? ld_t : R) : R;
   dim3 grid(ceil_div(cols, 32), ceil_div(rows, 32));
-  cast_act_kernel<<<grid, 256, 0, st>>>(in, ld_in, R, C, reinterpret_cast<bf16*>(out), out_lo_off, ld_out,
+  DSVG_CUDA(launch_k(cast_act_kernel, grid, dim3(256), 0, st, in, ld_in, R, C, reinterpret_cast<bf16*>(out), out_lo_off, ld_out,
                                         reinterpret_cast<bf16*>(outT), outT_lo_off, ld_t,
                                         reinterpret_cast<const bf16*>(mask), mask_lo_off, ld_mask, mask_scale,
-                                        make_dropout(drop_p, drop_site, seed));
+                                        make_dropout(drop_p, drop_site, seed)));
   ++g_launches;
-  DSVG_LAUNCH_CHECK();
   return 0;
 }
 
@@ -126,10 +131,9 @@ extern "C" int dsvg_seg_sum(const float* in, int nseq, int L, int d, dsvg_bf16* 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int grid = ceil_div((long long)nseq * d, 256);
   if (grid > 148 * 8) grid = 148 * 8;
-  seg_sum_kernel<<<grid, 256, 0, st>>>(in, nseq, L, d, reinterpret_cast<bf16*>(out), out_lo_off, out_f32,
-                                       make_dropout(drop_p, drop_site, seed));
+  DSVG_CUDA(launch_k(seg_sum_kernel, dim3(grid), dim3(256), 0, st, in, nseq, L, d, reinterpret_cast<bf16*>(out), out_lo_off, out_f32,
+                                       make_dropout(drop_p, drop_site, seed)));
   ++g_launches;
-  DSVG_LAUNCH_CHECK();
   return 0;
 }
 
@@ -158,8 +162,7 @@ extern "C" int dsvg_add_f32(const float* a, const float* b, float* y, size_t n, 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int grid = ceil_div((long long)n, 256);
   if (grid > 148 * 8) grid = 148 * 8;
-  add_f32_kernel<<<grid, 256, 0, st>>>(a, b, y, n);
+  DSVG_CUDA(launch_k(add_f32_kernel, dim3(grid), dim3(256), 0, st, a, b, y, n));
   ++g_launches;
-  DSVG_LAUNCH_CHECK();
   return 0;
 }

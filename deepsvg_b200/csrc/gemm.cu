@@ -35,6 +35,10 @@ void set_error(const char* fmt, ...) {
 }
 const char* last_error() { return g_err; }
 unsigned long long g_launches = 0;
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("DSVG_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
 static uint32_t g_outer_lbo = 0, g_outer_sbo = 0;  // debug override of the MN-major descriptor strides
 
 // ------------------------------------------------------------------------------------------------
@@ -621,10 +625,12 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     tmem_alloc(tmem_slot, Cfg::kTmemCols);
     tmem_relinquish();
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above touched only this CTA's shared memory / TMEM
 
   const int m_tiles = (M + kBlockM - 1) / kBlockM;
   const int n_tiles = (N + BN - 1) / BN;
@@ -849,10 +855,12 @@ outer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   // bf16 1.0 everywhere: the layout of an all-ones operand is irrelevant, only the descriptor must be valid
   for (int i = threadIdx.x; i < Cfg::kOnesBytes / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;
   fence_proxy_async_smem();
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above touched only this CTA's shared memory / TMEM
 
   const int q_tiles = (Q + BQ - 1) / BQ;
   const bool do_colsum = colsum_out != nullptr && (blockIdx.x % q_tiles) == 0;
@@ -996,9 +1004,9 @@ static int launch_linear_mode(const CUtensorMap& a, const CUtensorMap& alo, cons
   }
   const int tiles = ceil_div(M, kBlockM) * ceil_div(N, BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  linear_kernel<BN, NPLANES, MODE><<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(a, alo, b, blo, c, M, N, K, ep);
+  DSVG_CUDA(launch_k(linear_kernel<BN, NPLANES, MODE>, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, st, a, alo, b, blo, c, M,
+                     N, K, ep));
   ++g_launches;
-  DSVG_LAUNCH_CHECK();
   return 0;
 }
 template <int BN>
@@ -1066,11 +1074,10 @@ static int launch_outer(const CUtensorMap& a, const CUtensorMap& alo, const CUte
   const int per = ceil_div(total_mblk, splits);
   splits = ceil_div(total_mblk, per);
   dim3 grid(out_tiles, splits);
-  outer_kernel<BQ, NPLANES><<<grid, kThreads, Cfg::kSmemBytes, st>>>(a, alo, b, blo, M, P, Q, per, alpha, alpha_dev, C, ldc, colsum_out,
-                                                                      g_outer_lbo ? g_outer_lbo : Cfg::kBoxBytes,
-                                                                      g_outer_sbo ? g_outer_sbo : 1024u);
+  DSVG_CUDA(launch_k(outer_kernel<BQ, NPLANES>, grid, dim3(kThreads), Cfg::kSmemBytes, st, a, alo, b, blo, M, P, Q, per, alpha,
+                     alpha_dev, C, ldc, colsum_out, g_outer_lbo ? g_outer_lbo : uint32_t(Cfg::kBoxBytes),
+                     g_outer_sbo ? g_outer_sbo : 1024u));
   ++g_launches;
-  DSVG_LAUNCH_CHECK();
   return 0;
 }
 

@@ -53,6 +53,8 @@ __global__ void __launch_bounds__(kLnWarps * 32)
 ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
               bf16* __restrict__ y, size_t y_lo, float* __restrict__ mean_out, float* __restrict__ rstd_out, int M,
               float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int D = NV * 128;
   const int lane = threadIdx.x & 31;
   const int warp = blockIdx.x * kLnWarps + (threadIdx.x >> 5);
@@ -89,6 +91,8 @@ __global__ void __launch_bounds__(kLnWarps * 32)
 ln_pool_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                    const uint8_t* __restrict__ valid, float* __restrict__ z, float* __restrict__ mean_out,
                    float* __restrict__ rstd_out, float* __restrict__ inv_cnt, int nseq, int L, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int D = NV * 128;
   const int lane = threadIdx.x & 31;
   const int warp = blockIdx.x * kLnWarps + (threadIdx.x >> 5);
@@ -165,6 +169,8 @@ struct LnBwdArgs {
 
 template <int NV>
 __global__ void __launch_bounds__(kLnWarps * 32) ln_bwd_kernel(LnBwdArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int D = NV * 128;
   constexpr float invD = 1.f / float(D);
   __shared__ float red[kLnWarps][D];
@@ -281,10 +287,9 @@ extern "C" int dsvg_ln_fwd(const float* x, const float* gamma, const float* beta
   DSVG_CHECK(x && gamma && beta && y && mean && rstd && M > 0, "dsvg_ln_fwd: bad arguments");
   DSVG_CHECK(D % 128 == 0, "dsvg_ln_fwd: d_model must be a multiple of 128");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  DSVG_LN_DISPATCH(D, (ln_fwd_kernel<NV><<<ln_grid(M), kLnWarps * 32, 0, st>>>(
-                          x, gamma, beta, reinterpret_cast<bf16*>(y), y_lo_off, mean, rstd, M, 1e-5f)));
+  DSVG_LN_DISPATCH(D, DSVG_CUDA(launch_k(ln_fwd_kernel<NV>, dim3(ln_grid(M)), dim3(kLnWarps * 32), 0, st, x, gamma, beta,
+                                         reinterpret_cast<bf16*>(y), y_lo_off, mean, rstd, M, 1e-5f)));
   ++g_launches;
-  DSVG_LAUNCH_CHECK();
   return 0;
 }
 
@@ -294,10 +299,9 @@ extern "C" int dsvg_ln_pool_fwd(const float* x, const float* gamma, const float*
              "dsvg_ln_pool_fwd: bad arguments");
   DSVG_CHECK(D % 128 == 0, "dsvg_ln_pool_fwd: d_model must be a multiple of 128");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  DSVG_LN_DISPATCH(D, (ln_pool_fwd_kernel<NV><<<ln_grid(nseq), kLnWarps * 32, 0, st>>>(
-                          x, gamma, beta, valid, z, mean, rstd, inv_cnt, nseq, L, 1e-5f)));
+  DSVG_LN_DISPATCH(D, DSVG_CUDA(launch_k(ln_pool_fwd_kernel<NV>, dim3(ln_grid(nseq)), dim3(kLnWarps * 32), 0, st, x, gamma,
+                                         beta, valid, z, mean, rstd, inv_cnt, nseq, L, 1e-5f)));
   ++g_launches;
-  DSVG_LAUNCH_CHECK();
   return 0;
 }
 
@@ -320,8 +324,7 @@ extern "C" int dsvg_ln_bwd(const float* x, const float* mean, const float* rstd,
   a.drop = make_dropout(drop_p, drop_site, seed);
   a.dgamma = dgamma; a.dbeta = dbeta; a.M = M;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  DSVG_LN_DISPATCH(D, (ln_bwd_kernel<NV><<<ln_grid(M), kLnWarps * 32, 0, st>>>(a)));
+  DSVG_LN_DISPATCH(D, DSVG_CUDA(launch_k(ln_bwd_kernel<NV>, dim3(ln_grid(M)), dim3(kLnWarps * 32), 0, st, a)));
   ++g_launches;
-  DSVG_LAUNCH_CHECK();
   return 0;
 }
