@@ -306,6 +306,50 @@ class SVGTransformer(nn.Module):
                 res[k]._dsvg_handle = handle
         return res
 
+    # -------------------------------------------------------------------------------------------------
+    # inference exit: what cfg.visualize (default_icons.py:79-97), the notebooks and the GUI call
+    # -------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def greedy_sample(self, commands_enc=None, args_enc=None, commands_dec=None, args_dec=None, label=None, z=None,
+                      hierarch_logits=None, concat_groups=True, temperature=0.0001):
+        """One-shot decoding (model.py:414-423): logits -> tokens -> validity masking.  The logits come from the CUDA
+        forward; the token post-processing below is a handful of tiny torch ops (not on the train-step hot path).
+        At the reference's default temperature (1e-4) `Categorical(logits / T).sample()` is an argmax up to exact
+        ties; temperatures below 1e-3 therefore take the deterministic argmax, larger ones sample."""
+        res = self.forward(commands_enc, args_enc, commands_dec, args_dec, label=label, z=z,
+                           hierarch_logits=hierarch_logits, return_tgt=False)
+
+        def pick(logits):
+            if temperature < 1e-3:
+                return logits.argmax(dim=-1)
+            return torch.distributions.Categorical(logits=logits / temperature).sample()
+
+        commands_y = pick(res["command_logits"])
+        args_y = pick(res["args_logits"]) - 1                               # shift back: class 0 is the -1 PAD value
+        visible = None
+        if self.cfg.decode_stages == 2:                                    # _threshold_sample, model/utils.py:82-84
+            visible = torch.softmax(res["visibility_logits"], dim=-1)[..., 1].squeeze(-1) > 0.7
+        commands_y, args_y = self._make_valid(commands_y, args_y, visible)
+        if concat_groups:                                                   # keep tokens before each path's first EOS
+            n = commands_y.size(0)
+            keep = (commands_y == 4).cumsum(dim=-1) == 0
+            commands_y = commands_y[keep].reshape(n, -1)
+            args_y = args_y[keep].reshape(n, -1, self.cfg.n_args)
+        return commands_y, args_y
+
+    def _make_valid(self, commands_y, args_y, visibility_y=None, PAD_VAL=-1):
+        """model.py:450-459: invisible paths become `m EOS EOS ...` with PAD arguments; argument slots a command does
+        not use (CMD_ARGS_MASK) become PAD."""
+        if visibility_y is not None:
+            blank = torch.full((commands_y.size(-1),), 4, dtype=commands_y.dtype, device=commands_y.device)
+            blank[0] = 0
+            hidden = ~visibility_y
+            commands_y = torch.where(hidden.unsqueeze(-1), blank, commands_y)
+            args_y = torch.where(hidden[..., None, None], torch.full_like(args_y, PAD_VAL), args_y)
+        used = self.cmd_args_mask[commands_y].bool()
+        args_y = torch.where(used, args_y, torch.full_like(args_y, PAD_VAL))
+        return commands_y, args_y
+
     # =================================================================================================
     # weights: fp32 master -> (split-)bf16 operand + transposed operand, refreshed when the parameter changes
     # =================================================================================================

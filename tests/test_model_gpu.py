@@ -182,3 +182,33 @@ def test_encode_mode_and_z_injection():
         out = model(None, None, None, None, z=z.view(3, 1, 1, -1), return_tgt=False)
         np.testing.assert_allclose(out["args_logits"].cpu().numpy(), ro["args_logits"].numpy(), rtol=1e-3, atol=1e-4)
         assert "tgt_commands" not in out
+
+
+def test_greedy_sample_matches_oracle_decoding():
+    """one-shot greedy decoding on top of the CUDA forward, against the same post-processing of the
+    oracle's logits (argmax, visibility threshold 0.7, CMD_ARGS_MASK, EOS truncation)."""
+    cfg = O.make_cfg("hierarchical", use_vae=False)
+    model, _, params = _build(cfg, "bf16x3")
+    cmd, arg = O.synth_batch(cfg, 3, seed=12)
+    c, a = cmd.to(DEV), arg.to(DEV)
+    cy, ay = model.greedy_sample(c, a, None, None, concat_groups=False)
+    ro = O.forward(params, cfg, cmd, arg)
+    rc, ra = ro["command_logits"].argmax(-1), ro["args_logits"].argmax(-1) - 1
+    vis = torch.softmax(ro["visibility_logits"], -1)[..., 1].squeeze(-1) > 0.7
+    blank = torch.full((rc.shape[-1],), 4)
+    blank[0] = 0
+    rc = torch.where(~vis[..., None], blank, rc)
+    ra = torch.where(~vis[..., None, None], torch.full_like(ra, -1), ra)
+    ra = torch.where(O.CMD_ARGS_MASK[rc].bool(), ra, torch.full_like(ra, -1))
+    # tokens must agree wherever the oracle's decision is not a tie at the parity tolerance
+    t2 = ro["command_logits"].topk(2, -1).values
+    sure_c = (t2[..., 0] - t2[..., 1]) > 2e-4
+    assert bool(((cy.cpu() == rc) | ~sure_c).all())
+    t2 = ro["args_logits"].topk(2, -1).values
+    sure_a = ((t2[..., 0] - t2[..., 1]) > 2e-4) & sure_c[..., None]
+    assert bool(((ay.cpu() == ra) | ~sure_a).all())
+    assert cy.shape == (3, 8, 31) and ay.shape == (3, 8, 31, 11)
+    # concat_groups=True keeps exactly the tokens before each path's first EOS (N = 1, as every reference caller uses it)
+    c1, a1 = model.greedy_sample(c[:1], a[:1], None, None)
+    k1, _ = model.greedy_sample(c[:1], a[:1], None, None, concat_groups=False)
+    assert c1.shape[0] == 1 and c1.shape[1] == int(((k1 == 4).cumsum(-1) == 0).sum()) and a1.shape[1:] == (c1.shape[1], 11)

@@ -1,0 +1,87 @@
+"""Turns gpurun_out/<round>_* (written by tools/gpu_artifacts.sh on the GPU box) into the tracked summaries under
+profiles/: launch shares of one train step, key ncu metrics of the dominant kernels, the bench lines."""
+import csv
+import collections
+import json
+import os
+import re
+import subprocess
+import sys
+
+R = sys.argv[1] if len(sys.argv) > 1 else "r1"
+OUT = "profiles"
+os.makedirs(OUT, exist_ok=True)
+
+
+def launches(path, last_n):
+    rows = list(csv.reader(open(path, errors="ignore")))
+    hdr = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+    H = rows[hdr]
+    ki, vi, ui = H.index("Kernel Name"), H.index("Metric Value"), H.index("Metric Unit")
+    data = []
+    for r in rows[hdr + 1:]:
+        if len(r) <= vi:
+            continue
+        name = re.sub(r"\(.*", "", r[ki]).replace("void ", "")
+        v = float(r[vi].replace(",", ""))
+        v = v / 1e3 if r[ui] == "ns" else (v * 1e3 if r[ui] == "ms" else v)
+        data.append((name, v))
+    data = data[-last_n:]
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for n, v in data:
+        agg[n][0] += 1
+        agg[n][1] += v
+    return data, agg
+
+
+WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__registers_per_thread", "dram__bytes_read.sum",
+        "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__m_xbar2l1tex_read_bytes.sum", "smsp__inst_executed.sum"]
+
+
+def ncu_raw(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    if len(rows) < 3:
+        return []
+    H, U = rows[0], rows[1]
+    res = []
+    for r in rows[2:]:
+        d = {"kernel": re.sub(r"\(.*", "", r[H.index("Kernel Name")])}
+        for w in WANT:
+            if w in H:
+                d[w] = r[H.index(w)] + " " + U[H.index(w)]
+        res.append(d)
+    return res
+
+
+def main():
+    g = "gpurun_out/%s_" % R
+    lines = []
+    bench = json.load(open(g + "bench_n1.json"))
+    ref = json.load(open(g + "bench_reference.json"))
+    json.dump(bench, open("%s/%s_bench_n1.json" % (OUT, R), "w"), indent=1)
+    json.dump(ref, open("%s/%s_bench_reference.json" % (OUT, R), "w"), indent=1)
+    n_per_step = int(round(bench["gpu_launches"])) + 25        # + torch fills / copies in the same step
+    data, agg = launches(g + "launches.csv", n_per_step)
+    tot = sum(a[1] for a in agg.values())
+    with open("%s/%s_launch_shares.txt" % (OUT, R), "w") as f:
+        f.write("# one train step (N=512) under `ncu --metrics gpu__time_duration.sum --clock-control none`: last %d launches\n"
+                "# (cold-cache, serialised: compare SHARES, not absolutes).  total %.0f us\n" % (len(data), tot))
+        for k, a in sorted(agg.items(), key=lambda x: -x[1][1]):
+            f.write("%9.0f us %5.1f%% %4d  %s\n" % (a[1], 100 * a[1] / tot, a[0], k))
+    for name in ("linear", "outer", "attn", "ln_bwd"):
+        rep = g + "prof_%s.ncu-rep" % name
+        if not os.path.exists(rep):
+            continue
+        with open("%s/%s_ncu_%s.txt" % (OUT, R, name), "w") as f:
+            f.write("# ncu --set full --clock-control none, selected raw metrics per captured launch (%s)\n" % rep)
+            for d in ncu_raw(rep):
+                f.write(json.dumps(d) + "\n")
+    print("wrote", sorted(os.listdir(OUT)))
+
+
+if __name__ == "__main__":
+    main()
