@@ -280,12 +280,19 @@ def run_ours(a):
     ops.PROFILE = [] if rank == 0 else None
     step(cmd_d, arg_d)              # every rank runs it: the step contains collectives
     torch.cuda.synchronize()
+    shapes = {}
     if rank == 0:
-        for family, flops, e0, e1 in ops.PROFILE:
+        for family, flops, e0, e1, shape in ops.PROFILE:
+            ms_k = e0.elapsed_time(e1)
             f = fam.setdefault(family, [0, 0.0, 0.0])
             f[0] += 1
             f[1] += flops
-            f[2] += e0.elapsed_time(e1)
+            f[2] += ms_k
+            if shape is not None:
+                g = shapes.setdefault((family,) + tuple(shape), [0, 0.0, 0.0])
+                g[0] += 1
+                g[1] += flops
+                g[2] += ms_k
     ops.PROFILE = None
 
     if rank != 0:
@@ -321,7 +328,12 @@ def run_ours(a):
                      "ms_per_step_in_kernel": lin[2], "traffic": None,
                      "step": {"achieved": step_tflops, "frac": step_tflops / sus, "gflop_per_icon": TRAIN_GFLOP_PER_ICON},
                      "families": {k: {"launches": v[0], "ms": v[2], "tflops": (v[1] / (v[2] / 1e3) / 1e12 if v[2] else 0)}
-                                  for k, v in fam.items()}},
+                                  for k, v in fam.items()},
+                     # the six most expensive GEMM shapes of the step, each with its own achieved rate (live CUDA events)
+                     "top_shapes": [{"kernel": k[0], "MNK": list(k[1:]), "launches": v[0], "ms": round(v[2], 4),
+                                     "tflops": round(v[1] / (v[2] / 1e3) / 1e12, 1),
+                                     "frac_of_peak": round(v[1] / (v[2] / 1e3) / 1e12 / sus, 3)}
+                                    for k, v in sorted(shapes.items(), key=lambda kv: -kv[1][2])[:6]]},
         "clocks": sampler.summary() if sampler else None,
     }
     if cpu_rate is not None:

@@ -577,14 +577,18 @@ struct LinearCfg {
   static constexpr int kBBytes = BN * kBlockK * 2;       // 16/32 KB
   static constexpr int kStageBytes = NPLANES * (kABytes + kBBytes);
   static constexpr int kStagingBytes = lin_tma_out(MODE) ? BN * kBlockM * 2 : kEpiWarps * kStageWarpBytes;
-  static constexpr int kStages = (212 * 1024 - kStagingBytes) / kStageBytes > 4 ? 4 : (212 * 1024 - kStagingBytes) / kStageBytes;
+  // BN = 128 single-plane kernels are sized so that TWO CTAs fit one SM (2 x 256 TMEM columns, <= 113 KB of shared
+  // memory and <= 102 registers each): twice the TMA loads in flight and twice the epilogue warps per SM.
+  static constexpr int kCtasPerSm = (BN == 128 && NPLANES == 1) ? 2 : 1;
+  static constexpr int kBudget = (kCtasPerSm == 2 ? 110 : 212) * 1024;
+  static constexpr int kStages = (kBudget - kStagingBytes) / kStageBytes > 4 ? 4 : (kBudget - kStagingBytes) / kStageBytes;
   static_assert(kStages >= 2, "linear: at least two pipeline stages must fit");
   static constexpr int kTmemCols = 2 * BN;  // two accumulator stages (256 or 512: powers of two)
   static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kStagingBytes + 256;
 };
 
 template <int BN, int NPLANES, int MODE>
-__global__ void __launch_bounds__((LinearCfg<BN, NPLANES, MODE>::kThreads), 1)
+__global__ void __launch_bounds__((LinearCfg<BN, NPLANES, MODE>::kThreads), (LinearCfg<BN, NPLANES, MODE>::kCtasPerSm))
 linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
               const __grid_constant__ CUtensorMap tmC, int M, int N, int K, Epi ep) {
@@ -1003,7 +1007,8 @@ static int launch_linear_mode(const CUtensorMap& a, const CUtensorMap& alo, cons
     configured = true;
   }
   const int tiles = ceil_div(M, kBlockM) * ceil_div(N, BN);
-  const int grid = tiles < sm_count() ? tiles : sm_count();
+  const int slots = sm_count() * Cfg::kCtasPerSm;
+  const int grid = tiles < slots ? tiles : slots;
   DSVG_CUDA(launch_k(linear_kernel<BN, NPLANES, MODE>, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, st, a, alo, b, blo, c, M,
                      N, K, ep));
   ++g_launches;
@@ -1135,7 +1140,8 @@ extern "C" int dsvg_linear(const dsvg_bf16* X, size_t x_lo_off, int lda, const d
     ep.vec = v ? (direct ? 2 : 1) : 0;
   }
   const bool split = x_lo_off != 0;
-  const bool wide = (N > 128) && !split;  // parity mode always uses the 128-wide tile (shared-memory budget)
+  static const bool force128 = [] { const char* e = getenv("DSVG_BN128"); return e && e[0] == '1'; }();
+  const bool wide = (N > 128) && !split && !force128;  // parity mode always uses the 128-wide tile (shared-memory budget)
   const uint32_t bn = wide ? 256 : 128;
   CUtensorMap a, alo, b, blo;
   const bf16* Xb = reinterpret_cast<const bf16*>(X);

@@ -22,8 +22,8 @@ PROFILE = None
 
 
 class _Prof:
-    def __init__(self, family, flops):
-        self.family, self.flops = family, flops
+    def __init__(self, family, flops, shape=None):
+        self.family, self.flops, self.shape = family, flops, shape
 
     def __enter__(self):
         if PROFILE is not None:
@@ -35,7 +35,7 @@ class _Prof:
     def __exit__(self, *a):
         if PROFILE is not None:
             self.e1.record()
-            PROFILE.append((self.family, self.flops, self.e0, self.e1))
+            PROFILE.append((self.family, self.flops, self.e0, self.e1, self.shape))
         return False
 
 
@@ -95,14 +95,14 @@ def linear(X, W, M, N, K, *, bias=None, scale_cols=0, scale=1.0, relu=False, dro
         ep.out_f32, ep.out_f32_ld = out_f32.data_ptr(), out_f32.stride(0)
     if out_act is not None:
         ep.out_act, ep.out_lo_off, ep.out_act_ld = out_act.ptr, out_act.lo, out_act.ld
-    with _Prof("linear", 2.0 * M * N * K):
+    with _Prof("linear", 2.0 * M * N * K, (M, N, K)):
         rc = _lib.load().dsvg_linear(X.ptr, X.lo, X.ld, W.ptr, W.lo, W.ld, M, N, K, C.byref(ep), _stream())
     _lib.check(rc, "dsvg_linear")
 
 
 def outer(A, B, M, P, Q, Cout, *, alpha=1.0, alpha_dev=None, colsum=None):
     """Cout[P,Q] += alpha * A[M,P]^T . B[M,Q]; Cout fp32 (row stride = Cout.stride(0)); colsum[P] += alpha * sum_rows A."""
-    with _Prof("outer", 2.0 * M * P * Q):
+    with _Prof("outer", 2.0 * M * P * Q, (M, P, Q)):
         rc = _lib.load().dsvg_outer(A.ptr, A.lo, A.ld, B.ptr, B.lo, B.ld, M, P, Q, alpha, _p(alpha_dev),
                                     Cout.data_ptr(), Cout.stride(0), _p(colsum), _stream())
     _lib.check(rc, "dsvg_outer")
