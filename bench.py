@@ -127,6 +127,12 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------------------------------------
+def host_threads():
+    """Threads given to the CPU arm: all host cores up to 32 -- beyond that torch's intra-op parallelism over these small
+    GEMMs (K = 256) only adds synchronisation (measured 38 s/step with 128 threads vs ~5 s with 32 on the same box)."""
+    return max(1, min(os.cpu_count() or 1, 32))
+
+
 def cpu_port_rate(batch, steps, warmup, threads):
     """The oracle (CPU restatement of the reference path) timed on the host cores: icons/s of fwd+loss+bwd."""
     from oracle import svg_oracle as O
@@ -148,7 +154,7 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     rate, dt = cpu_port_rate(a.cpu_batch, a.steps, a.warmup, threads)
     sample = "oracle port (eval-mode arithmetic, fp32 torch CPU), hierarchical_ordered, batch %d per step, best of %d" % (
         a.cpu_batch, a.steps)
@@ -305,7 +311,7 @@ def run_ours(a):
     step_tflops = ips * TRAIN_GFLOP_PER_ICON / 1e3 / world
     lin = fam.get("linear", [1, 0.0, 1.0])
     lin_tflops = lin[1] / (lin[2] / 1e3) / 1e12 if lin[2] > 0 else 0.0
-    cpu_threads = os.cpu_count() or 1
+    cpu_threads = host_threads()
     cpu_rate, cpu_dt = (None, None)
     if world == 1 and not a.no_cpu_baseline:
         cpu_rate, cpu_dt = cpu_port_rate(a.cpu_batch, 2, 1, cpu_threads)
