@@ -10,6 +10,7 @@ from .config import (Hierarchical, HierarchicalSelfMatching, OneStageOneShot, Sk
                      _DefaultConfig)
 from .loss import SVGLoss  # noqa: F401
 from .model import SVGTransformer  # noqa: F401
+from .optim import FusedAdamW  # noqa: F401
 
 __all__ = ["SVGTransformer", "SVGLoss", "Hierarchical", "OneStageOneShot", "HierarchicalSelfMatching", "SketchRNN",
-           "Sketchformer", "_DefaultConfig"]
+           "Sketchformer", "_DefaultConfig", "FusedAdamW"]

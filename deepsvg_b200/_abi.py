@@ -40,4 +40,6 @@ SIGNATURES = {
     "dsvg_gather_rows": (I, [P, P, I, I, P, Z, P]),
     "dsvg_scatter_rows": (I, [P, P, I, I, P, P]),
     "dsvg_add_f32": (I, [P, P, P, Z, P]),
+    "dsvg_grad_sqnorm": (I, [P, I, I, P, P]),
+    "dsvg_adamw_step": (I, [P, I, I, F, F, F, F, F, F, F, F, P, P]),
 }

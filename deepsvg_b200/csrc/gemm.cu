@@ -1141,7 +1141,10 @@ extern "C" int dsvg_linear(const dsvg_bf16* X, size_t x_lo_off, int lda, const d
   }
   const bool split = x_lo_off != 0;
   static const bool force128 = [] { const char* e = getenv("DSVG_BN128"); return e && e[0] == '1'; }();
-  const bool wide = (N > 128) && !split && !force128;  // parity mode always uses the 128-wide tile (shared-memory budget)
+  // 256-wide tiles for the big path-level GEMMs; the group-level ones (M = N_icons * 8 rows, a few dozen tiles) run the
+  // 128-wide kernel: twice the CTAs and two CTAs per SM shorten their latency-bound critical path.  Parity mode always
+  // uses the 128-wide tile (shared-memory budget of the split planes).
+  const bool wide = (N > 128) && !split && !force128 && M > 16384;
   const uint32_t bn = wide ? 256 : 128;
   CUtensorMap a, alo, b, blo;
   const bf16* Xb = reinterpret_cast<const bf16*>(X);

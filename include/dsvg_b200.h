@@ -160,6 +160,15 @@ int dsvg_gather_rows(const float* table, const long long* idx, int n, int w, dsv
 int dsvg_scatter_rows(const float* g, const long long* idx, int n, int w, float* dtable, void* stream);
 int dsvg_add_f32(const float* a, const float* b, float* y, size_t n, void* stream);
 
+/* ---- optimiser step on a table of tensors (config.py:64-65, train.py:99-102) ------------ */
+/* table: DEVICE array of n_tensors rows {float* param; const float* grad; float* exp_avg; float* exp_avg_sq;
+ * long long numel}.  max_chunks = ceil(max numel / 4096) capped by the caller (grid.x). */
+int dsvg_grad_sqnorm(const void* table, int n_tensors, int max_chunks, float* out_sq, void* stream);
+/* AdamW (decoupled weight decay), gradients scaled by min(1, max_norm / (sqrt(*grad_sqnorm_dev) + 1e-6)) when max_norm > 0 */
+int dsvg_adamw_step(const void* table, int n_tensors, int max_chunks, float lr, float beta1, float beta2, float eps,
+                    float weight_decay, float bias_corr1, float bias_corr2, float max_norm, const float* grad_sqnorm_dev,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

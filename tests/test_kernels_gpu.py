@@ -446,3 +446,22 @@ def test_cast_transpose_and_labels():
     gr = _rand(40, 64, seed=3)
     ops.scatter_rows(gr, idx, 40, 64, dt)
     assert _rel(dt, torch.zeros(52, 64, device=DEV).index_add_(0, idx, gr)) < 1e-5
+
+
+def test_fused_adamw_matches_torch():
+    """multi-tensor AdamW + global-norm clipping vs torch.optim.AdamW + clip_grad_norm_."""
+    from deepsvg_b200 import FusedAdamW
+    shapes = [(257, 64), (256,), (768, 256), (7, 256), (2827, 256), (1,)]
+    ref = [torch.nn.Parameter(_rand(*s, seed=i)) for i, s in enumerate(shapes)]
+    mine = [torch.nn.Parameter(p.detach().clone()) for p in ref]
+    o_ref = torch.optim.AdamW(ref, lr=2e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2)
+    o_mine = FusedAdamW(mine, lr=2e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_grad_norm=1.0)
+    for step in range(4):
+        for i, (a, b) in enumerate(zip(ref, mine)):
+            g = _rand(*a.shape, seed=100 * step + i, scale=0.3 if step % 2 else 3.0)
+            a.grad, b.grad = g.clone(), g.clone()
+        torch.nn.utils.clip_grad_norm_(ref, 1.0)
+        o_ref.step()
+        o_mine.step()
+        for a, b in zip(ref, mine):
+            assert _rel(b.detach(), a.detach()) < 2e-6
