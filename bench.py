@@ -73,8 +73,12 @@ class ClockSampler(threading.Thread):
             pynvml.nvmlInit()
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(gpu))
+            # one-off firmware queries, synchronously and long before any timed region (they can take 100s of ms and
+            # stall kernel submission while they run)
+            self.mx = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.first = self._reasons()
         except Exception:
-            self.nv = None
+            self.nv, self.h = None, None
 
     @staticmethod
     def _physical_index(i):
@@ -101,11 +105,7 @@ class ClockSampler(threading.Thread):
         if self.h is None:
             return
         nv = self.nv
-        try:
-            mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
-        except Exception:
-            mx = 0
-        first = self._reasons()
+        mx, first = self.mx, self.first
         while not self.stop_flag:
             try:
                 clk = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
@@ -113,7 +113,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append((clk, mx, 0))
             except Exception:
                 pass
-            time.sleep(0.25)
+            time.sleep(0.5)
         last = self._reasons()
         self.rows.append((self.rows[-1][0] if self.rows else 0, mx, first | last))
 
@@ -220,6 +220,9 @@ def run_ours(a):
         torch.cuda.synchronize()
 
     def timed(fn, steps):
+        import gc
+        gc.collect()
+        gc.disable()     # a generation-2 collection in the launching thread shows up as a 30-100 ms hole in the GPU queue
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         marks = []
@@ -241,6 +244,7 @@ def run_ours(a):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = t.item()
         barrier()
+        gc.enable()
         return ms
 
     for _ in range(max(a.warmup, 3)):
