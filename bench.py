@@ -225,20 +225,29 @@ def run_ours(a):
         gc.disable()     # a generation-2 collection in the launching thread shows up as a 30-100 ms hole in the GPU queue
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        marks = []
+        marks, host = [], []
+        trace = bool(os.environ.get("DSVG_BENCH_TRACE"))
+        st0 = torch.cuda.memory_stats() if trace else None
         e0.record()
         for _ in range(steps):
+            h0 = time.perf_counter()
             fn()
-            if os.environ.get("DSVG_BENCH_TRACE"):
+            if trace:
                 ev = torch.cuda.Event(enable_timing=True)
                 ev.record()
                 marks.append(ev)
+                host.append((time.perf_counter() - h0) * 1e3)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         if marks and rank == 0:
             ts = [e0.elapsed_time(m) for m in marks]
+            st1 = torch.cuda.memory_stats()
             sys.stderr.write("per-step ms: " + " ".join("%.1f" % (b - a) for a, b in zip([0.0] + ts[:-1], ts)) + "\n")
+            sys.stderr.write("host-side ms: " + " ".join("%.1f" % h for h in host) + "\n")
+            sys.stderr.write("allocator: cudaMalloc +%d, retries +%d, segments %d\n" % (
+                st1["num_device_alloc"] - st0["num_device_alloc"], st1["num_alloc_retries"] - st0["num_alloc_retries"],
+                st1["segment.all.current"]))
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -254,23 +263,28 @@ def run_ours(a):
         sampler.start()      # its one-off NVML firmware queries happen during the warm-up below, not in the timed region
     # Extended warm-up (untimed): the caching allocator needs a few more iterations to reach its steady-state pool, and
     # with NCCL peer mappings every late cudaMalloc costs 100-250 ms (measured as isolated spikes at N=2).  Continue
-    # until three consecutive steps are within 10 % of the fastest seen (at most 24 extra steps, same count on all ranks).
+    # until five consecutive steps are within 10 % of the fastest seen AND trigger no new cudaMalloc (the default allocator
+    # was measured to keep adding segments for ~80 steps: 238 cudaMallocs inside one 40-step timed region, each a
+    # 20-350 ms hole); at most 120 extra steps, same count on all ranks.
     stable, best, extra = 0, None, 0
-    while extra < 24:
+    n_malloc = torch.cuda.memory_stats()["num_device_alloc"]
+    while extra < 120:
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record()
         step(cmd_d, arg_d)
         step_e2e()
         t1.record()
         torch.cuda.synchronize()
-        dt = torch.tensor([t0.elapsed_time(t1)], device=dev)
+        now_malloc = torch.cuda.memory_stats()["num_device_alloc"]
+        dt = torch.tensor([t0.elapsed_time(t1), float(now_malloc - n_malloc)], device=dev)
+        n_malloc = now_malloc
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        dt = dt.item()
+        dt, grew = dt[0].item(), dt[1].item() > 0
         best = dt if best is None else min(best, dt)
-        stable = stable + 1 if dt <= 1.1 * best else 0
+        stable = stable + 1 if (dt <= 1.1 * best and not grew) else 0   # steady = fast AND no new device allocation
         extra += 1
-        if stable >= 3 and extra >= 4:
+        if stable >= 5 and extra >= 6:
             break
     if sampler:
         sampler.recording = True
