@@ -155,9 +155,15 @@ def run_reference(a):
     if rank != 0:
         return
     threads = host_threads()
-    rate, dt = cpu_port_rate(a.cpu_batch, a.steps, a.warmup, threads)
+    # bounded sample: probe one small step, then size the per-step batch so that W + K steps take about two minutes
+    _, t_probe = cpu_port_rate(4, 1, 0, threads)
+    budget_s = 120.0
+    per_icon = t_probe / 4.0
+    batch = int(max(2, min(64, budget_s / (max(1, a.steps + a.warmup) * per_icon))))
+    a.cpu_batch = batch
+    rate, dt = cpu_port_rate(batch, a.steps, a.warmup, threads)
     sample = "oracle port (eval-mode arithmetic, fp32 torch CPU), hierarchical_ordered, batch %d per step, best of %d" % (
-        a.cpu_batch, a.steps)
+        batch, a.steps)
     line = {"impl": "reference", "metric": "icons/sec train-step (fwd+loss+bwd) hierarchical_ordered", "value": rate,
             "unit": "icons/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
