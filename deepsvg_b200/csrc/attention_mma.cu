@@ -129,12 +129,18 @@ __device__ __forceinline__ void dropout_tile(float (&mult)[2][4][4], const Dropo
 #pragma unroll
     for (int hrow = 0; hrow < 2; ++hrow) {
       const int i = 16 * mt + g + 8 * hrow;
-      const unsigned long long base = ((pair * 32 + i) * 4 + t) * 4;  // index of the first pair of draws
+      // draws 8 * ((pair * 32 + i) * 4 + t) .. + 7  =  two whole quads (see common.cuh): word nt covers elements
+      // (nt >> 1 selects the quad, nt & 1 its a / b finaliser)
+      const unsigned long long quad = ((pair * 32 + i) * 4 + t) * 2;
+      const uint32_t hk = drop_hikey(d, quad), q0 = uint32_t(quad);   // quad is even: q0 + 1 cannot carry
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        const uint32_t h = dropout_bits(d, base + nt);
-        mult[mt][nt][2 * hrow] = (h & 0xFFFFu) >= d.thr16 ? d.scale : 0.f;
-        mult[mt][nt][2 * hrow + 1] = (h >> 16) >= d.thr16 ? d.scale : 0.f;
+      for (int hq = 0; hq < 2; ++hq) {
+        const uint32_t s1 = drop_stage1(q0 + hq, hk);
+        const uint32_t a = drop_fin_a(s1), b = drop_fin_b(s1);
+        mult[mt][2 * hq][2 * hrow] = drop_keep_lo(a, d.thr16) ? d.scale : 0.f;
+        mult[mt][2 * hq][2 * hrow + 1] = drop_keep_hi(a, d.thr16) ? d.scale : 0.f;
+        mult[mt][2 * hq + 1][2 * hrow] = drop_keep_lo(b, d.thr16) ? d.scale : 0.f;
+        mult[mt][2 * hq + 1][2 * hrow + 1] = drop_keep_hi(b, d.thr16) ? d.scale : 0.f;
       }
     }
 }

@@ -83,12 +83,19 @@ __device__ __forceinline__ void act_store2(bf16* p, size_t lo_off, size_t i, flo
 }
 
 // ----------------------------------------------------------------------------------------------
-// Dropout masks: stateless counter-based generator.  A dropout call site is (seed, site id); element i of the site's
-// tensor draws the 16-bit half (i & 1) of  mix32( (i >> 1) * odd ^ key(seed, site) )  and is kept iff draw >= thr16.
-// mix32 is the "lowbias32" integer finaliser (2 multiplies, 3 xor-shifts): ~4 integer ops per element, so that the
-// masks generated inside the GEMM epilogues cost less than the stores they gate (a Philox4x32-10 version measured
-// 2 k instructions per 32x32 chunk and made the epilogue issue-bound).  The backward pass regenerates the same draws.
-// The drop probability is quantised to thr16 / 65536 and the survivors are scaled by its exact complement.
+// Dropout masks: stateless counter-based generator.  A dropout call site is (seed, site id).  Elements are numbered
+// i = 0, 1, 2, ... inside the site's tensor; the four elements of "quad" q = i >> 2 share one first mixing stage
+//     s = xs15( xs16( q * 0x9E3779B1 ^ key' ) * 0x7feb352d )           key' = key(seed, site) ^ (q >> 32) * 0x85EBCA77
+// (the first half of the "lowbias32" integer finaliser) and two finalisers
+//     a = xs16( s * 0x846ca68b )   -> elements 4q (low 16 bits) and 4q + 1 (high 16 bits)
+//     b = xs16( s * 0xC2B2AE35 )   -> elements 4q + 2 and 4q + 3
+// An element is kept iff its 16-bit draw >= thr16; survivors are scaled by the exact complement of thr16 / 65536.
+// Cost: 13 integer instructions per four draws.  The masks are generated inside the GEMM epilogues, where every
+// instruction counts: ncu showed the previous one-hash-per-two-elements version at 62 % of the FFN1 epilogue's
+// instructions (and a Philox4x32-10 version before it at 2 k instructions per 32x32 chunk).  Marginal keep rates,
+// pairwise joint rates inside a quad and at lags 1..1024, and byte histograms of the draws were checked against
+// their binomial / chi-square expectations on 2^24 quads for several keys (tools/check_dropout_hash.py).
+// The backward pass regenerates the same draws from (seed, site, index).
 // ----------------------------------------------------------------------------------------------
 struct Dropout {
   float p;             // requested drop probability; 0 disables
@@ -109,28 +116,46 @@ inline Dropout make_dropout(float p, uint32_t site, unsigned long long seed) {
   d.key = host_mix32(uint32_t(seed) ^ host_mix32(uint32_t(seed >> 32) + 0x9E3779B9u * (site + 1u)));
   return d;
 }
-__device__ __forceinline__ uint32_t mix32(uint32_t x) {
-  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+// key' for a quad index (the high word is zero for every tensor below 2^34 elements, but stays part of the definition)
+__device__ __forceinline__ uint32_t drop_hikey(const Dropout& d, unsigned long long quad) {
+  return (uint32_t(quad >> 32) * 0x85EBCA77u) ^ d.key;
+}
+__device__ __forceinline__ uint32_t drop_stage1(uint32_t quad_lo, uint32_t hikey) {
+  uint32_t x = (quad_lo * 0x9E3779B1u) ^ hikey;
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15;
   return x;
 }
-// 32 random bits shared by elements 2*pair and 2*pair + 1
+__device__ __forceinline__ uint32_t drop_fin_a(uint32_t s) { s *= 0x846ca68bu; return s ^ (s >> 16); }
+__device__ __forceinline__ uint32_t drop_fin_b(uint32_t s) { s *= 0xC2B2AE35u; return s ^ (s >> 16); }
+// keep tests on the two halves of a 32-bit word of draws.  thr_hi = thr16 << 16: (h >> 16) >= thr16 <=> h >= thr_hi.
+__device__ __forceinline__ bool drop_keep_lo(uint32_t h, uint32_t thr16) { return (h & 0xFFFFu) >= thr16; }
+__device__ __forceinline__ bool drop_keep_hi(uint32_t h, uint32_t thr16) { return h >= (thr16 << 16); }
+// 32 random bits shared by elements 2*pair and 2*pair + 1 (low / high half)
 __device__ __forceinline__ uint32_t dropout_bits(const Dropout& d, unsigned long long pair) {
-  return mix32((uint32_t(pair) * 0x9E3779B1u) ^ (uint32_t(pair >> 32) * 0x85EBCA77u) ^ d.key);
+  const unsigned long long quad = pair >> 1;
+  const uint32_t s = drop_stage1(uint32_t(quad), drop_hikey(d, quad));
+  return (pair & 1) ? drop_fin_b(s) : drop_fin_a(s);
 }
 // multiplier (0 or scale) for a single element
 __device__ __forceinline__ float dropout_mult(const Dropout& d, unsigned long long idx) {
   if (d.p <= 0.f) return 1.f;
-  uint32_t h = dropout_bits(d, idx >> 1);
-  uint32_t draw = (idx & 1) ? (h >> 16) : (h & 0xFFFFu);
-  return draw >= d.thr16 ? d.scale : 0.f;
+  const uint32_t h = dropout_bits(d, idx >> 1);
+  const bool keep = (idx & 1) ? drop_keep_hi(h, d.thr16) : drop_keep_lo(h, d.thr16);
+  return keep ? d.scale : 0.f;
+}
+// multipliers for the 4 elements of quad `quad` (elements 4*quad .. 4*quad + 3)
+__device__ __forceinline__ float4 dropout_quad_mult(const Dropout& d, uint32_t quad_lo, uint32_t hikey) {
+  const uint32_t s = drop_stage1(quad_lo, hikey);
+  const uint32_t a = drop_fin_a(s), b = drop_fin_b(s);
+  const float sc = d.scale;
+  return make_float4(drop_keep_lo(a, d.thr16) ? sc : 0.f, drop_keep_hi(a, d.thr16) ? sc : 0.f,
+                     drop_keep_lo(b, d.thr16) ? sc : 0.f, drop_keep_hi(b, d.thr16) ? sc : 0.f);
 }
 // multipliers for 4 consecutive elements starting at idx (idx % 4 == 0)
 __device__ __forceinline__ float4 dropout_mult4(const Dropout& d, unsigned long long idx) {
   if (d.p <= 0.f) return make_float4(1.f, 1.f, 1.f, 1.f);
-  const uint32_t h0 = dropout_bits(d, idx >> 1), h1 = dropout_bits(d, (idx >> 1) + 1);
-  const float s = d.scale;
-  return make_float4((h0 & 0xFFFFu) >= d.thr16 ? s : 0.f, (h0 >> 16) >= d.thr16 ? s : 0.f,
-                     (h1 & 0xFFFFu) >= d.thr16 ? s : 0.f, (h1 >> 16) >= d.thr16 ? s : 0.f);
+  const unsigned long long quad = idx >> 2;
+  return dropout_quad_mult(d, uint32_t(quad), drop_hikey(d, quad));
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -145,6 +145,8 @@ struct Epi {
   int out_act_ld;
   int vec;   // 1: every pointer/stride satisfies the 4-wide vector path
   int mode;  // 0: generic run-time epilogue; k > 0: lean epilogue kLeanFeat[k - 1]
+  long long* dbg;  // development trace (dsvg_debug_linear_trace): per-tile clock64 stamps of CTA 0, or null
+  int exp;   // EXPERIMENT ONLY (DSVG_EXP): bit0 skip B loads, bit1 skip A loads after a CTA's first tile (wrong results)
 };
 
 constexpr int kThreads = 192;       // 6 warps
@@ -397,7 +399,8 @@ __device__ __forceinline__ void lean_prefetch(LeanPre<FEAT>& p, int lane, int ro
 
 template <uint32_t FEAT>
 __device__ __forceinline__ void epilogue_chunk_lean(uint32_t (&v)[32], uint32_t stage_addr, int lane, int row0, int col0,
-                                                    int M, int N, const Epi& ep, const LeanPre<FEAT>& pre) {
+                                                    int M, int N, const Epi& ep, const LeanPre<FEAT>& pre,
+                                                    const float4& bias_in) {
   {
     const uint32_t my = stage_addr + lane * (kStageRow * 4);
 #pragma unroll
@@ -409,8 +412,7 @@ __device__ __forceinline__ void epilogue_chunk_lean(uint32_t (&v)[32], uint32_t 
   const int cg = lane & 7, rsub = lane >> 3;
   const int col = col0 + 4 * cg;
   if (col < N) {
-    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if constexpr (FEAT & F_BIAS) bias4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
+    const float4 bias4 = bias_in;   // fetched by the caller at the top of the tile (off the chunk's critical path)
     float accs = 1.f;
     if constexpr (FEAT & F_ACCS) accs = __ldg(ep.acc_scale_dev);
     const int r_first = row0 + rsub;
@@ -421,6 +423,8 @@ __device__ __forceinline__ void epilogue_chunk_lean(uint32_t (&v)[32], uint32_t 
     const bool has_rv = (FEAT & F_ROWVEC) && ep.rowvec != nullptr;
     const bool has_drop = (FEAT & F_DROP) && ep.drop.p > 0.f;
     const uint32_t lds_base = stage_addr + (rsub * kStageRow + 4 * cg) * 4;
+    // dropout quad index of (r_first, col); N % 4 == 0 and col % 4 == 0 on this path
+    const unsigned long long quad0 = ((unsigned long long)r_first * (unsigned long long)N + (unsigned long long)col) >> 2;
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int row = r_first + 4 * it;
@@ -436,7 +440,8 @@ __device__ __forceinline__ void epilogue_chunk_lean(uint32_t (&v)[32], uint32_t 
         }
         if constexpr (FEAT & F_DROP) {
           if (has_drop) {
-            float4 m = dropout_mult4(ep.drop, (unsigned long long)row * (unsigned long long)N + col);
+            const unsigned long long quad = quad0 + (unsigned long long)it * (unsigned long long)N;   // row advances by 4
+            const float4 m = dropout_quad_mult(ep.drop, uint32_t(quad), drop_hikey(ep.drop, quad));
             x.x *= m.x; x.y *= m.y; x.z *= m.z; x.w *= m.w;
           }
         }
@@ -489,23 +494,23 @@ constexpr int kNumLean = sizeof(kLeanFeat) / sizeof(kLeanFeat[0]);
 // ------------------------------------------------------------------------------------------------
 template <uint32_t FEAT>
 __device__ __forceinline__ void tma_out_chunk(uint32_t (&v)[32], uint8_t* out_tile, int r, long long grow, int gc0, int c,
-                                              int M, int N, const Epi& ep, const uint4 (&mk)[4]) {
+                                              int M, int N, const Epi& ep, const uint4 (&mk)[4], uint32_t bias_sm) {
   float x[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
   if constexpr (FEAT & F_BIAS) {
+    // bias_sm holds bias[n0 .. n0 + BN) (zero past N), staged once per n-tile by the epilogue warps: broadcast LDS.128
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      if (gc0 + 4 * q < N) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + gc0 + 4 * q));
-        x[4 * q] += b.x; x[4 * q + 1] += b.y; x[4 * q + 2] += b.z; x[4 * q + 3] += b.w;
-      }
+      const float4 b = ld_shared_v4(bias_sm + (c + 4 * q) * 4);
+      x[4 * q] += b.x; x[4 * q + 1] += b.y; x[4 * q + 2] += b.z; x[4 * q + 3] += b.w;
     }
   }
   if constexpr (FEAT & F_SCALE) {
+    if (gc0 < ep.scale_cols) {   // scale_cols % 32 == 0 (pick_mode): the whole chunk is scaled or none of it
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (gc0 + j < ep.scale_cols) x[j] *= ep.scale;
+      for (int j = 0; j < 32; ++j) x[j] *= ep.scale;
+    }
   }
   if constexpr (FEAT & F_RELU) {
 #pragma unroll
@@ -513,12 +518,19 @@ __device__ __forceinline__ void tma_out_chunk(uint32_t (&v)[32], uint8_t* out_ti
   }
   if constexpr (FEAT & F_DROP) {
     if (ep.drop.p > 0.f) {
-      const unsigned long long base = (unsigned long long)grow * (unsigned long long)N + (unsigned long long)gc0;  // even
+      // 32 consecutive elements starting at a multiple of 8 (N % 8 == 0, gc0 % 32 == 0): 8 quads whose low index
+      // word cannot carry, so key' is computed once
+      const unsigned long long qb = ((unsigned long long)grow * (unsigned long long)N + (unsigned long long)gc0) >> 2;
+      const uint32_t hk = drop_hikey(ep.drop, qb), q0 = uint32_t(qb), thr = ep.drop.thr16;
+      const float sc = ep.drop.scale;
 #pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        const uint32_t h = dropout_bits(ep.drop, (base >> 1) + q);
-        x[2 * q] *= (h & 0xFFFFu) >= ep.drop.thr16 ? ep.drop.scale : 0.f;
-        x[2 * q + 1] *= (h >> 16) >= ep.drop.thr16 ? ep.drop.scale : 0.f;
+      for (int q = 0; q < 8; ++q) {
+        const uint32_t s1 = drop_stage1(q0 + q, hk);
+        const uint32_t a = drop_fin_a(s1), b = drop_fin_b(s1);
+        x[4 * q] = drop_keep_lo(a, thr) ? x[4 * q] * sc : 0.f;
+        x[4 * q + 1] = drop_keep_hi(a, thr) ? x[4 * q + 1] * sc : 0.f;
+        x[4 * q + 2] = drop_keep_lo(b, thr) ? x[4 * q + 2] * sc : 0.f;
+        x[4 * q + 3] = drop_keep_hi(b, thr) ? x[4 * q + 3] * sc : 0.f;
       }
     }
   }
@@ -565,9 +577,17 @@ __device__ __forceinline__ void tma_out_load_mask(uint4 (&mk)[4], long long grow
 // ------------------------------------------------------------------------------------------------
 // warp 0 TMA, warp 1 MMA, then E epilogue warps (E/4 per TMEM lane quarter).  The store-only lean epilogues (modes 1-3)
 // are latency-bound on the TMEM -> smem -> global chain and need few registers, so they run 16 warps; the others 8.
-__host__ __device__ constexpr int lin_epi_warps(int mode, int bn) { return 8; }
+__host__ __device__ constexpr int lin_epi_warps(int mode, int bn) {
+  // the fp32-residual epilogues (modes 4, 6) are stall-bound chains of shared / global accesses with no single hot
+  // spot (ncu: issue slots 29 % busy with 2 warps per scheduler): the 256-wide, one-CTA-per-SM kernel runs them 16 wide
+  return ((mode == 4 || mode == 6) && bn == 256) ? 16 : 8;
+}
 // act-output lean modes write their bf16 tile through shared memory with one TMA store per 64-column box
 __host__ __device__ constexpr bool lin_tma_out(int mode) { return mode == 1 || mode == 2 || mode == 3 || mode == 5; }
+
+__device__ __forceinline__ void trace_stamp(const Epi& ep, int it, int slot, int lane) {
+  if (ep.dbg != nullptr && blockIdx.x == 0 && lane == 0 && it < 16) ep.dbg[it * 16 + slot] = clock64();
+}
 
 template <int BN, int NPLANES, int MODE = 0>
 struct LinearCfg {
@@ -584,7 +604,8 @@ struct LinearCfg {
   static constexpr int kStages = (kBudget - kStagingBytes) / kStageBytes > 4 ? 4 : (kBudget - kStagingBytes) / kStageBytes;
   static_assert(kStages >= 2, "linear: at least two pipeline stages must fit");
   static constexpr int kTmemCols = 2 * BN;  // two accumulator stages (256 or 512: powers of two)
-  static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kStagingBytes + 256;
+  static constexpr int kBiasBytes = BN * 4;   // bias slice of the current n-tile (TMA-out epilogues)
+  static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kStagingBytes + 256 + kBiasBytes;
 };
 
 template <int BN, int NPLANES, int MODE>
@@ -604,6 +625,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   uint64_t* tfull_bar = bars + 2 * Cfg::kStages;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;            // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* bias_sm = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kStagingBytes + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -645,16 +667,45 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     // =================== TMA producer (warp-uniform control flow, one elected lane issues) ===================
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    int pit = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++pit) {
       const int m0 = (tile / n_tiles) * kBlockM;
       const int n0 = (tile % n_tiles) * BN;
+      trace_stamp(ep, pit, 0, lane);
+      if constexpr (MODE > 0) {
+        // the epilogue's own global operands (fp32 residual rows, bf16 ReLU/dropout mask rows) are pulled into L2 now,
+        // about one tile period before the epilogue warps load them: their loads then pay L2 instead of DRAM latency
+        constexpr uint32_t FEAT = kLeanFeat[MODE > 0 ? MODE - 1 : 0];
+        if constexpr ((FEAT & (F_RES | F_MASK)) != 0) {
+          const int rows = (M - m0) < kBlockM ? (M - m0) : kBlockM;
+          const int cols = (N - n0) < BN ? (N - n0) : BN;
+          for (int r = lane; r < rows; r += 32) {
+            if constexpr (FEAT & F_RES)
+              prefetch_l2_bulk(ep.residual + size_t(m0 + r) * ep.res_ld + n0, uint32_t(cols) * 4u);
+            if constexpr (FEAT & F_MASK)
+              prefetch_l2_bulk(ep.mask + size_t(m0 + r) * ep.mask_ld + n0, uint32_t(cols) * 2u);
+          }
+        }
+      }
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (kb == num_kb - 1) trace_stamp(ep, pit, 1, lane);
         if (elect_one()) {
           uint8_t* st = tiles + stage * Cfg::kStageBytes;
+          if (NPLANES == 1 && ep.exp != 0 && tile != int(blockIdx.x)) {
+            const bool la = !(ep.exp & 2), lb = !(ep.exp & 1);
+            if (!la && !lb) {
+              mbar_arrive(&full_bar[stage]);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[stage], (la ? Cfg::kABytes : 0) + (lb ? Cfg::kBBytes : 0));
+              if (la) tma_load_2d(st, &tmA, &full_bar[stage], kb * kBlockK, m0);
+              if (lb) tma_load_2d(st + Cfg::kABytes, &tmB, &full_bar[stage], kb * kBlockK, n0);
+            }
+          } else {
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           tma_load_2d(st, &tmA, &full_bar[stage], kb * kBlockK, m0);
           tma_load_2d(st + Cfg::kABytes, &tmB, &full_bar[stage], kb * kBlockK, n0);
+          }
           if (NPLANES == 2) {
             tma_load_2d(st + Cfg::kABytes + Cfg::kBBytes, &tmAlo, &full_bar[stage], kb * kBlockK, m0);
             tma_load_2d(st + 2 * Cfg::kABytes + Cfg::kBBytes, &tmBlo, &full_bar[stage], kb * kBlockK, n0);
@@ -676,12 +727,16 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      trace_stamp(ep, it, 2, lane);
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
+      trace_stamp(ep, it, 3, lane);
       const uint32_t d_tmem = tmem_base + acc * BN;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
+        if (kb == 0) trace_stamp(ep, it, 4, lane);
+        if (kb == num_kb - 1) trace_stamp(ep, it, 5, lane);
         if (elect_one()) {
           const uint32_t a_hi = smem_u32(tiles + stage * Cfg::kStageBytes);
           const uint32_t b_hi = a_hi + Cfg::kABytes;
@@ -703,6 +758,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete
         }
         __syncwarp();
+        if (kb == num_kb - 1) trace_stamp(ep, it, 6, lane);
         if (++stage == Cfg::kStages) {
           stage = 0;
           phase ^= 1;
@@ -715,12 +771,14 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     const int half = (warp - 2) >> 2;     // which 32-column chunk of every kCols-wide pass this warp drains
     const uint32_t stage_buf = smem_u32(staging) + (warp - 2) * kStageWarpBytes;
     int it = 0;
+    int bias_n0 = -1;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int m0 = (tile / n_tiles) * kBlockM;
       const int n0 = (tile % n_tiles) * BN;
       const long long row0 = (long long)m0 + quarter * 32;
+      if (warp == 2) trace_stamp(ep, it, 8, lane);
       if constexpr (MODE == 0) {
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
@@ -733,62 +791,99 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           epilogue_chunk<false>(v, stage_buf, lane, row0, n0 + c, M, N, ep, 1.f, nullptr, 0);
         }
       } else if constexpr (lin_tma_out(MODE)) {
+        // Streamed TMA-store epilogue.  A "pass" = all epilogue warps draining kCols accumulator columns into their
+        // 64-column boxes of the staging tile; each pass ends with ONE named barrier after which an elected thread
+        // bulk-stores the pass's boxes as one group.  Box reuse: the boxes of pass ci were last stored kPasses groups
+        // ago, so before the barrier of pass ci - 1 the storing thread waits until at most kPasses - 2 groups are still
+        // reading shared memory; the TMA engine therefore streams tile t's boxes out while tile t + 1 is drained.
         constexpr uint32_t FEAT = kLeanFeat[MODE > 0 ? MODE - 1 : 0];
+        constexpr int kPasses = BN / kCols;
+        static_assert(kPasses >= 2, "streamed TMA-store epilogue needs at least two passes per tile");
         uint8_t* out_tile = reinterpret_cast<uint8_t*>(staging);
         const int r = quarter * 32 + lane;
         const long long grow = (long long)m0 + r;
         uint4 mk[2][4];
         tma_out_load_mask<FEAT>(mk[0], grow, n0 + half * 32, M, N, ep);
-        // the previous tile's bulk stores must have finished reading the staging tile before it is overwritten
-        if (warp == 2 && lane == 0) tma_store_wait_read();
-        named_bar_sync(1, Cfg::kEpiWarps * 32);
+        if constexpr (FEAT & F_BIAS) {
+          if (n0 != bias_n0) {   // same decision in every epilogue warp (they walk the same tile sequence)
+            const int et = threadIdx.x - 64;
+            named_bar_sync(2, Cfg::kEpiWarps * 32);        // nobody still reads the previous slice
+            for (int j = et; j < BN; j += Cfg::kEpiWarps * 32) bias_sm[j] = (n0 + j < N) ? __ldg(ep.bias + n0 + j) : 0.f;
+            named_bar_sync(2, Cfg::kEpiWarps * 32);
+            bias_n0 = n0;
+          }
+        }
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
+        if (warp == 2) trace_stamp(ep, it, 10, lane);
 #pragma unroll
-        for (int ci = 0; ci < BN / kCols; ++ci) {
+        for (int ci = 0; ci < kPasses; ++ci) {
           const int c = half * 32 + kCols * ci;
           if (n0 + c < N) {
             uint32_t v[32];
             tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * BN + c), v);
-            if (ci + 1 < BN / kCols) tma_out_load_mask<FEAT>(mk[(ci + 1) & 1], grow, n0 + c + kCols, M, N, ep);
+            if (ci + 1 < kPasses) tma_out_load_mask<FEAT>(mk[(ci + 1) & 1], grow, n0 + c + kCols, M, N, ep);
             tmem_ld_wait();
-            tma_out_chunk<FEAT>(v, out_tile, r, grow, n0 + c, c, M, N, ep, mk[ci & 1]);
+            tma_out_chunk<FEAT>(v, out_tile, r, grow, n0 + c, c, M, N, ep, mk[ci & 1], smem_u32(bias_sm));
+          }
+          if (ci == kPasses - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (warp == 2) trace_stamp(ep, it, 11, lane);
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);   // TMEM stage drained: the MMA warp may start tile it + 2
+          }
+          fence_proxy_async_smem();                          // generic-proxy smem writes -> visible to the TMA engine
+          if (warp == 2 && lane == 0) tma_store_wait_read_n<(kPasses - 2)>();   // next pass's boxes are free again
+          named_bar_sync(1, Cfg::kEpiWarps * 32);
+          if (warp == 2 && lane == 0) {
+#pragma unroll
+            for (int bx = ci * (kCols / 64); bx < (ci + 1) * (kCols / 64); ++bx)
+              if (n0 + 64 * bx < N) tma_store_2d(&tmC, out_tile + bx * (kBlockM * 128), n0 + 64 * bx, m0);
+            tma_store_commit();
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);     // TMEM stage drained: the MMA warp may start tile it + 2
-        fence_proxy_async_smem();                          // generic-proxy smem writes -> visible to the TMA engine
-        named_bar_sync(1, Cfg::kEpiWarps * 32);
-        if (warp == 2 && lane == 0) {
-#pragma unroll
-          for (int bx = 0; bx < BN / 64; ++bx)
-            if (n0 + 64 * bx < N) tma_store_2d(&tmC, out_tile + bx * (kBlockM * 128), n0 + 64 * bx, m0);
-          tma_store_commit();
-        }
+        if (warp == 2) trace_stamp(ep, it, 12, lane);
         continue;
       } else {
         constexpr uint32_t FEAT = kLeanFeat[MODE > 0 ? MODE - 1 : 0];
         // residual / mask operands are fetched one chunk ahead: the first chunk's loads fly while the MMAs of this
         // tile are still running, the others while the previous chunk is being written out
-        LeanPre<FEAT> pre[2];
+        // (the 16-warp configuration has 96 registers per thread: one prefetch buffer, refilled right after its last
+        // use; its four warps per scheduler cover the shorter prefetch distance)
+        constexpr int kPre = Cfg::kEpiWarps > 8 ? 1 : 2;
+        LeanPre<FEAT> pre[kPre];
         lean_prefetch<FEAT>(pre[0], lane, int(row0), n0 + half * 32, M, N, ep);
+        // this lane's bias columns of every chunk of the tile: the shared-memory carve-out leaves L1 too small to keep
+        // the bias vector resident next to the residual stream, so a per-chunk load paid L2 latency on the critical path
+        float4 bias_pre[BN / kCols];
+#pragma unroll
+        for (int ci = 0; ci < BN / kCols; ++ci) {
+          bias_pre[ci] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if constexpr (FEAT & F_BIAS) {
+            const int bc = n0 + half * 32 + kCols * ci + 4 * (lane & 7);
+            if (bc < N) bias_pre[ci] = __ldg(reinterpret_cast<const float4*>(ep.bias + bc));
+          }
+        }
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
+        if (warp == 2) trace_stamp(ep, it, 10, lane);
 #pragma unroll
         for (int ci = 0; ci < BN / kCols; ++ci) {
           const int c = half * 32 + kCols * ci;
           if (n0 + c < N) {
             uint32_t v[32];
             tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * BN + c), v);
-            if (ci + 1 < BN / kCols) lean_prefetch<FEAT>(pre[(ci + 1) & 1], lane, int(row0), n0 + c + kCols, M, N, ep);
+            if (kPre == 2 && ci + 1 < BN / kCols)
+              lean_prefetch<FEAT>(pre[(ci + 1) & 1], lane, int(row0), n0 + c + kCols, M, N, ep);
             tmem_ld_wait();
-            epilogue_chunk_lean<FEAT>(v, stage_buf, lane, int(row0), n0 + c, M, N, ep, pre[ci & 1]);
+            epilogue_chunk_lean<FEAT>(v, stage_buf, lane, int(row0), n0 + c, M, N, ep, pre[ci & (kPre - 1)], bias_pre[ci]);
+            if (kPre == 1 && ci + 1 < BN / kCols) lean_prefetch<FEAT>(pre[0], lane, int(row0), n0 + c + kCols, M, N, ep);
           }
         }
       }
       tc_fence_before();
       __syncwarp();
+      if (warp == 2) trace_stamp(ep, it, 11, lane);
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
     if constexpr (lin_tma_out(MODE)) {
@@ -1049,7 +1144,7 @@ static int pick_mode(const Epi& ep, bool split, int N) {
     const uint32_t optional = have & (F_DROP | F_ROWVEC);   // run-time checked inside the lean code
     if ((f & ~optional) == (have & ~optional) && (f & ~have) == 0) {
       if (lin_tma_out(k + 1)) {
-        const bool ok = N % 8 == 0 && ep.out_act_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(ep.out_act) & 15) == 0 &&
+        const bool ok = N % 8 == 0 && ep.out_act_ld % 8 == 0 && ep.scale_cols % 32 == 0 && (reinterpret_cast<uintptr_t>(ep.out_act) & 15) == 0 &&
                         (!ep.mask || (ep.mask_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(ep.mask) & 15) == 0)) &&
                         (!ep.bias || (reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0);
         if (!ok) return 0;
@@ -1097,6 +1192,9 @@ extern "C" void dsvg_debug_outer_desc(unsigned lbo, unsigned sbo) {
   dsvg::g_outer_sbo = sbo;
 }
 extern "C" unsigned long long dsvg_launch_count(void) { return dsvg::g_launches; }
+// development aid (not in the public header): subsequent dsvg_linear launches write per-tile clock stamps of CTA 0
+static long long* g_linear_trace = nullptr;
+extern "C" void dsvg_debug_linear_trace(long long* dev_buf_256) { g_linear_trace = dev_buf_256; }
 
 extern "C" int dsvg_linear(const dsvg_bf16* X, size_t x_lo_off, int lda, const dsvg_bf16* W, size_t w_lo_off, int ldb,
                            int M, int N, int K, const dsvg_epilogue* e, void* stream) {
@@ -1129,6 +1227,11 @@ extern "C" int dsvg_linear(const dsvg_bf16* X, size_t x_lo_off, int lda, const d
   ep.out_lo_off = e->out_lo_off;
   ep.out_act_ld = e->out_act_ld;
   DSVG_CHECK(ep.out_f32 || ep.out_act, "dsvg_linear: no output requested");
+  {
+    static const int exp_flags = [] { const char* s = getenv("DSVG_EXP"); return s ? atoi(s) : 0; }();
+    ep.exp = exp_flags;
+    ep.dbg = g_linear_trace;
+  }
   {
     auto al = [](const void* p, size_t a) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % a) == 0; };
     bool v = (N % 4 == 0) && al(ep.bias, 16) && al(ep.rowvec, 16) && al(ep.residual, 16) && al(ep.out_f32, 16) &&

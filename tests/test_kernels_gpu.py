@@ -225,11 +225,13 @@ def test_attention_fwd_bwd(L, H, hd, masked):
     assert _rel(dqkv.float(), qv.grad) < 1e-4
 
 
-@pytest.mark.parametrize("L,masked", [(32, True), (31, False), (8, True), (17, True)])
-def test_attention_mma_fast_path(L, masked):
-    """Single-plane bf16, head_dim 32, L <= 32 -> the mma.sync kernel; P and dS are rounded to bf16 inside."""
+@pytest.mark.parametrize("L,masked,nseq", [(32, True, 61), (31, False, 61), (8, True, 61), (17, True, 61),
+                                           (31, True, 1500), (8, True, 2600)])
+def test_attention_mma_fast_path(L, masked, nseq):
+    """Single-plane bf16, head_dim 32, L <= 32 -> the mma.sync kernels; P and dS are rounded to bf16 inside.
+    The large nseq cases make every CTA of the block-per-sequence kernels loop over several sequences."""
     ops = _ops()
-    H, hd, nseq = 8, 32, 61
+    H, hd = 8, 32
     d, M = H * hd, nseq * L
     qa = ops.act_from_float(_rand(M, 3 * d, seed=1, scale=0.7), 1)
     qv = qa.float().clone().requires_grad_(True)
