@@ -580,7 +580,7 @@ __device__ __forceinline__ void tma_out_load_mask(uint4 (&mk)[4], long long grow
 __host__ __device__ constexpr int lin_epi_warps(int mode, int bn) {
   // the fp32-residual epilogues (modes 4, 6) are stall-bound chains of shared / global accesses with no single hot
   // spot (ncu: issue slots 29 % busy with 2 warps per scheduler): the 256-wide, one-CTA-per-SM kernel runs them 16 wide
-  return ((mode == 4 || mode == 6) && bn == 256) ? 16 : 8;
+  return ((mode == 3 || mode == 4 || mode == 5 || mode == 6) && bn == 256) ? 16 : 8;
 }
 // act-output lean modes write their bf16 tile through shared memory with one TMA store per 64-column box
 __host__ __device__ constexpr bool lin_tma_out(int mode) { return mode == 1 || mode == 2 || mode == 3 || mode == 5; }
@@ -672,21 +672,6 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       const int m0 = (tile / n_tiles) * kBlockM;
       const int n0 = (tile % n_tiles) * BN;
       trace_stamp(ep, pit, 0, lane);
-      if constexpr (MODE > 0) {
-        // the epilogue's own global operands (fp32 residual rows, bf16 ReLU/dropout mask rows) are pulled into L2 now,
-        // about one tile period before the epilogue warps load them: their loads then pay L2 instead of DRAM latency
-        constexpr uint32_t FEAT = kLeanFeat[MODE > 0 ? MODE - 1 : 0];
-        if constexpr ((FEAT & (F_RES | F_MASK)) != 0) {
-          const int rows = (M - m0) < kBlockM ? (M - m0) : kBlockM;
-          const int cols = (N - n0) < BN ? (N - n0) : BN;
-          for (int r = lane; r < rows; r += 32) {
-            if constexpr (FEAT & F_RES)
-              prefetch_l2_bulk(ep.residual + size_t(m0 + r) * ep.res_ld + n0, uint32_t(cols) * 4u);
-            if constexpr (FEAT & F_MASK)
-              prefetch_l2_bulk(ep.mask + size_t(m0 + r) * ep.mask_ld + n0, uint32_t(cols) * 2u);
-          }
-        }
-      }
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (kb == num_kb - 1) trace_stamp(ep, pit, 1, lane);

@@ -96,10 +96,6 @@ template <int N>
 __device__ __forceinline__ void tma_store_wait_read_n() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
-// start moving `bytes` (multiple of 16) at a 16-byte aligned global address into L2; no destination, no completion
-__device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
-}
 // all committed bulk stores are complete (global writes performed)
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {

@@ -58,3 +58,8 @@ run("FFN1 (mode 3)", M, 512, 256, bias=bias512, relu=True, drop=(0.1, 3, 7), out
 run("dgrad (mode 1) K=512", M, 256, 512, out_act=out256)
 run("QKV (mode 2)", M, 768, 256, bias=bias768, scale_cols=256, scale=0.17, out_act=out768)
 run("out-proj (mode 4)", M, 256, 256, bias=bias256, drop=(0.1, 4, 7), residual=res, out_f32=outf)
+mk = ops.Act(M, 512, 1, dev, zero=True)
+mk.t.normal_()
+run("dgrad through mask (mode 5)", M, 512, 256, mask=mk, mask_scale=1.1, out_act=out512)
+x2 = torch.zeros(M, 256, device=dev)
+run("FFN2 (mode 4) K=512", M, 256, 512, bias=bias256, drop=(0.1, 4, 7), residual=x2, out_f32=x2)
