@@ -389,7 +389,9 @@ __device__ __forceinline__ void lean_prefetch(LeanPre<FEAT>& p, int lane, int ro
       for (int it = 0; it < 8; ++it) {
         const int row = row0 + rsub + 4 * it;
         if (row < M) {
-          if constexpr (FEAT & F_RES) p.res[it] = *reinterpret_cast<const float4*>(ep.residual + size_t(row) * ep.res_ld + col);
+          if constexpr (FEAT & F_RES)
+            p.res[it] = ep.residual != nullptr ? *reinterpret_cast<const float4*>(ep.residual + size_t(row) * ep.res_ld + col)
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
           if constexpr (FEAT & F_MASK) p.msk[it] = *reinterpret_cast<const uint2*>(ep.mask + size_t(row) * ep.mask_ld + col);
         }
       }
@@ -846,7 +848,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           bias_pre[ci] = make_float4(0.f, 0.f, 0.f, 0.f);
           if constexpr (FEAT & F_BIAS) {
             const int bc = n0 + half * 32 + kCols * ci + 4 * (lane & 7);
-            if (bc < N) bias_pre[ci] = __ldg(reinterpret_cast<const float4*>(ep.bias + bc));
+            if (bc < N && ep.bias != nullptr) bias_pre[ci] = __ldg(reinterpret_cast<const float4*>(ep.bias + bc));
           }
         }
         mbar_wait(&tfull_bar[acc], acc_phase);
@@ -885,6 +887,35 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   }
 }
 
+// 16-byte vector reduction (REDG.E.ADD.F32x4): four consecutive fp32 gradient entries per instruction
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// one 32 x 32 accumulator chunk of the weight-gradient tile -> C[row0.., col0..] += alpha * chunk.
+// Transposed through shared memory so that 8 lanes cover one 128-byte row segment; vector path needs ldc % 4 == 0,
+// Q % 4 == 0 and a 16-byte aligned C.
+__device__ __forceinline__ void outer_chunk_vec(uint32_t (&v)[32], uint32_t stage_addr, int lane, int row0, int col0,
+                                                int P, int Q, float alpha, float* C, int ldc) {
+  const uint32_t my = stage_addr + lane * (kStageRow * 4);
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    st_shared_v4(my + q * 16, __uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                 __uint_as_float(v[4 * q + 3]));
+  __syncwarp();
+  const int cg = lane & 7, rsub = lane >> 3;
+  const int col = col0 + 4 * cg;
+  if (col < Q) {
+    float* cp = C + size_t(row0 + rsub) * ldc + col;
+    const uint32_t lds_base = stage_addr + (rsub * kStageRow + 4 * cg) * 4;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const float4 x = ld_shared_v4(lds_base + it * (4 * kStageRow * 4));
+      if (row0 + rsub + 4 * it < P) red_add_v4(cp + size_t(4 * it) * ldc, x.x * alpha, x.y * alpha, x.z * alpha, x.w * alpha);
+    }
+  }
+  __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------------
 // dsvg_outer kernel (MN-major operands): one output tile [128 x BQ] per CTA, contraction over an M range
 // ------------------------------------------------------------------------------------------------
@@ -897,22 +928,27 @@ struct OuterCfg {
   static constexpr int kStages = (NPLANES == 1) ? 4 : 2;
   static constexpr int kTmemCols = 2 * BQ;  // BQ accumulator columns + 64 for the column-sum (bias) tile, power of 2
   static constexpr int kOnesBytes = 4096;   // 16 K-rows x 128 B of bf16 1.0 (B operand of the column-sum MMA) + slack
-  static constexpr int kStagingBytes = 4 * kStageWarpBytes;
+  // 8 epilogue warps (two per TMEM lane quarter, each draining half of the BQ columns).  Their transposition buffers
+  // alias the operand stages: when the accumulator barrier fires every TMA load has landed and every MMA has retired.
+  static constexpr int kEpiWarps = 8;
+  static constexpr int kThreads = 64 + 32 * kEpiWarps;
+  static constexpr int kStagingBytes = 0;
+  static_assert(kEpiWarps * kStageWarpBytes <= kStages * kStageBytes, "outer: staging must fit in the operand stages");
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kOnesBytes + kStagingBytes + 256;
 };
 
 template <int BQ, int NPLANES>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__((OuterCfg<BQ, NPLANES>::kThreads), 1)
 outer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
              const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo, int M, int P, int Q,
              int mblk_per_split, float alpha, const float* alpha_dev, float* C, int ldc, float* colsum_out,
-             uint32_t lbo, uint32_t sbo) {
+             uint32_t lbo, uint32_t sbo, int vec) {
   using Cfg = OuterCfg<BQ, NPLANES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* tiles = smem;
   uint8_t* ones = smem + Cfg::kStages * Cfg::kStageBytes;  // 1024-aligned
-  float* staging = reinterpret_cast<float*>(ones + Cfg::kOnesBytes);
+  float* staging = reinterpret_cast<float*>(tiles);   // epilogue only, after the main loop (see OuterCfg)
   uint64_t* bars = reinterpret_cast<uint64_t*>(ones + Cfg::kOnesBytes + Cfg::kStagingBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + Cfg::kStages;
@@ -1030,20 +1066,22 @@ outer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else {
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;      // which half of the BQ accumulator columns this warp drains
     const uint32_t stage_buf = smem_u32(staging) + (warp - 2) * kStageWarpBytes;
+    if (alpha_dev != nullptr) alpha *= __ldg(alpha_dev);
     mbar_wait(tfull_bar, 0);
     tc_fence_after();
     Epi dummy{};
-    if (alpha_dev != nullptr) alpha *= __ldg(alpha_dev);
 #pragma unroll 1
-    for (int c = 0; c < BQ; c += 32) {
+    for (int c = half * (BQ / 2); c < (half + 1) * (BQ / 2); c += 32) {
       if (q0 + c >= Q) break;
       uint32_t v[32];
       tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(c), v);
       tmem_ld_wait();
-      epilogue_chunk<true>(v, stage_buf, lane, (long long)p0 + quarter * 32, q0 + c, P, Q, dummy, alpha, C, ldc);
+      if (vec) outer_chunk_vec(v, stage_buf, lane, p0 + quarter * 32, q0 + c, P, Q, alpha, C, ldc);
+      else epilogue_chunk<true>(v, stage_buf, lane, (long long)p0 + quarter * 32, q0 + c, P, Q, dummy, alpha, C, ldc);
     }
-    if (do_colsum) {  // column 0 of the [128 x 64] tile = sum over this CTA's rows of A[:, p]
+    if (do_colsum && half == 0) {  // column 0 of the [128 x 64] tile = sum over this CTA's rows of A[:, p]
       uint32_t v[32];
       tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(BQ), v);
       tmem_ld_wait();
@@ -1126,7 +1164,9 @@ static int pick_mode(const Epi& ep, bool split, int N) {
   if ((f & F_SCALE) && ep.scale_cols % 4 != 0) return 0;
   for (int k = 0; k < kNumLean; ++k) {
     const uint32_t have = kLeanFeat[k];
-    const uint32_t optional = have & (F_DROP | F_ROWVEC);   // run-time checked inside the lean code
+    // steps that the lean code checks at run time (warp-uniform branches): dropout, row vector; and for the fp32 output
+    // mode 4 also bias and residual, so that it covers the latent / group-level "global" linears and their dgrads
+    const uint32_t optional = have & (F_DROP | F_ROWVEC | ((have & F_OUTF) && !(have & F_ACCS) ? (F_BIAS | F_RES) : 0u));
     if ((f & ~optional) == (have & ~optional) && (f & ~have) == 0) {
       if (lin_tma_out(k + 1)) {
         const bool ok = N % 8 == 0 && ep.out_act_ld % 8 == 0 && ep.scale_cols % 32 == 0 && (reinterpret_cast<uintptr_t>(ep.out_act) & 15) == 0 &&
@@ -1159,9 +1199,10 @@ static int launch_outer(const CUtensorMap& a, const CUtensorMap& alo, const CUte
   const int per = ceil_div(total_mblk, splits);
   splits = ceil_div(total_mblk, per);
   dim3 grid(out_tiles, splits);
-  DSVG_CUDA(launch_k(outer_kernel<BQ, NPLANES>, grid, dim3(kThreads), Cfg::kSmemBytes, st, a, alo, b, blo, M, P, Q, per, alpha,
+  DSVG_CUDA(launch_k(outer_kernel<BQ, NPLANES>, grid, dim3(Cfg::kThreads), Cfg::kSmemBytes, st, a, alo, b, blo, M, P, Q, per, alpha,
                      alpha_dev, C, ldc, colsum_out, g_outer_lbo ? g_outer_lbo : uint32_t(Cfg::kBoxBytes),
-                     g_outer_sbo ? g_outer_sbo : 1024u));
+                     g_outer_sbo ? g_outer_sbo : 1024u,
+                     int(ldc % 4 == 0 && Q % 4 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0)));
   ++g_launches;
   return 0;
 }

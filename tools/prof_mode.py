@@ -37,3 +37,21 @@ elif which == "mask":
     go(M, 512, 256, mask=mk, mask_scale=1.1, out_act=ops.Act(M, 512, 1, dev))
 elif which == "dgrad":
     go(M, 256, 512, out_act=ops.Act(M, 256, 1, dev))
+elif which == "small_outer":
+    Ms = 4096
+    A = ops.Act(Ms, 768, 1, dev, zero=True)
+    A.t.normal_()
+    B = ops.Act(Ms, 256, 1, dev, zero=True)
+    B.t.normal_()
+    Cw = torch.zeros(768, 256, device=dev)
+    cs = torch.zeros(768, device=dev)
+    for _ in range(4):
+        ops.outer(A, B, Ms, 768, 256, Cw, colsum=cs)
+    torch.cuda.synchronize()
+elif which == "small_generic":
+    g2 = torch.zeros(512, 256, device=dev)
+    go(512, 256, 256, bias=torch.zeros(256, device=dev), drop=(0.1, 4, 7), rowvec=g2, rows_per_group=1,
+       out_f32=torch.zeros(512, 256, device=dev))
+elif which == "small_lean":
+    x = torch.zeros(4096, 256, device=dev)
+    go(4096, 256, 256, bias=torch.zeros(256, device=dev), drop=(0.1, 4, 7), residual=x, out_f32=x)
