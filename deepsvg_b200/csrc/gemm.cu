@@ -146,7 +146,6 @@ struct Epi {
   int vec;   // 1: every pointer/stride satisfies the 4-wide vector path
   int mode;  // 0: generic run-time epilogue; k > 0: lean epilogue kLeanFeat[k - 1]
   long long* dbg;  // development trace (dsvg_debug_linear_trace): per-tile clock64 stamps of CTA 0, or null
-  int exp;   // EXPERIMENT ONLY (DSVG_EXP): bit0 skip B loads, bit1 skip A loads after a CTA's first tile (wrong results)
 };
 
 constexpr int kThreads = 192;       // 6 warps
@@ -679,20 +678,9 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         if (kb == num_kb - 1) trace_stamp(ep, pit, 1, lane);
         if (elect_one()) {
           uint8_t* st = tiles + stage * Cfg::kStageBytes;
-          if (NPLANES == 1 && ep.exp != 0 && tile != int(blockIdx.x)) {
-            const bool la = !(ep.exp & 2), lb = !(ep.exp & 1);
-            if (!la && !lb) {
-              mbar_arrive(&full_bar[stage]);
-            } else {
-              mbar_arrive_expect_tx(&full_bar[stage], (la ? Cfg::kABytes : 0) + (lb ? Cfg::kBBytes : 0));
-              if (la) tma_load_2d(st, &tmA, &full_bar[stage], kb * kBlockK, m0);
-              if (lb) tma_load_2d(st + Cfg::kABytes, &tmB, &full_bar[stage], kb * kBlockK, n0);
-            }
-          } else {
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           tma_load_2d(st, &tmA, &full_bar[stage], kb * kBlockK, m0);
           tma_load_2d(st + Cfg::kABytes, &tmB, &full_bar[stage], kb * kBlockK, n0);
-          }
           if (NPLANES == 2) {
             tma_load_2d(st + Cfg::kABytes + Cfg::kBBytes, &tmAlo, &full_bar[stage], kb * kBlockK, m0);
             tma_load_2d(st + 2 * Cfg::kABytes + Cfg::kBBytes, &tmBlo, &full_bar[stage], kb * kBlockK, n0);
@@ -1253,11 +1241,7 @@ extern "C" int dsvg_linear(const dsvg_bf16* X, size_t x_lo_off, int lda, const d
   ep.out_lo_off = e->out_lo_off;
   ep.out_act_ld = e->out_act_ld;
   DSVG_CHECK(ep.out_f32 || ep.out_act, "dsvg_linear: no output requested");
-  {
-    static const int exp_flags = [] { const char* s = getenv("DSVG_EXP"); return s ? atoi(s) : 0; }();
-    ep.exp = exp_flags;
-    ep.dbg = g_linear_trace;
-  }
+  ep.dbg = g_linear_trace;
   {
     auto al = [](const void* p, size_t a) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % a) == 0; };
     bool v = (N % 4 == 0) && al(ep.bias, 16) && al(ep.rowvec, 16) && al(ep.residual, 16) && al(ep.out_f32, 16) &&

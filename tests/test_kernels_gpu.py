@@ -62,12 +62,14 @@ def test_linear_full_epilogue():
     assert _rel(oa.float(), ref) < 2e-4
 
 
-@pytest.mark.parametrize("mode", ["dgrad", "qkv", "ffn1", "resid", "mask", "head_dgrad"])
-@pytest.mark.parametrize("N", [256, 768, 128])
-def test_linear_lean_epilogues(mode, N):
-    """The compile-time specialised epilogues (one per GEMM role of the model) against the same fp32 restatement."""
+@pytest.mark.parametrize("mode", ["dgrad", "qkv", "ffn1", "resid", "mask", "head_dgrad", "bias_f32", "res_f32"])
+@pytest.mark.parametrize("M,N", [(1000, 256), (1000, 768), (1000, 128), (16650, 256), (16650, 768), (33000, 512)])
+def test_linear_lean_epilogues(mode, M, N):
+    """The compile-time specialised epilogues (one per GEMM role of the model) against the same fp32 restatement.
+    M = 1000: the 128-wide, two-CTAs-per-SM kernels; M > 16384: the 256-wide persistent kernels (streamed bulk stores,
+    16 epilogue warps for the fp32 / mask modes), with a ragged last row tile and several tiles per CTA."""
     ops = _ops()
-    M, K, rpg = 1000, 256, 25
+    K, rpg = 256, 25
     X, W = _rand(M, K, seed=1), _rand(N, K, seed=2, scale=K ** -0.5)
     b, res, rv = _rand(N, seed=3), _rand(M, N, seed=4), _rand(M // rpg, N, seed=5)
     msk = torch.relu(_rand(M, N, seed=6))
@@ -97,6 +99,13 @@ def test_linear_lean_epilogues(mode, N):
     elif mode == "mask":
         ops.linear(xa, wa, M, N, K, mask=ma, mask_scale=1.25, out_act=oa)
         ref, got = acc * (ma.float() != 0) * 1.25, oa.float()
+    elif mode == "bias_f32":     # linear_global / VAE heads: bias only, fp32 out (lean mode 4 without residual)
+        ops.linear(xa, wa, M, N, K, bias=b, out_f32=of)
+        ref, got = acc + b, of
+    elif mode == "res_f32":      # dgrad accumulated into an fp32 gradient (lean mode 4 without bias)
+        of.copy_(res)
+        ops.linear(xa, wa, M, N, K, residual=of, out_f32=of)
+        ref, got = acc + res, of
     else:
         ops.linear(xa, wa, M, N, K, acc_scale=sc, residual=res, out_f32=of)
         ref, got = acc * 0.37 + res, of
@@ -127,7 +136,8 @@ def test_linear_dropout_statistics_and_determinism():
 
 
 @pytest.mark.parametrize("planes", [1, 2])
-@pytest.mark.parametrize("M,P,Q", [(4096, 768, 256), (1000, 300, 200), (2048, 2827, 64), (992, 7, 256), (130, 256, 512)])
+@pytest.mark.parametrize("M,P,Q", [(4096, 768, 256), (1000, 300, 200), (2048, 2827, 64), (992, 7, 256), (130, 256, 512),
+                                   (640, 100, 30), (20000, 512, 256)])   # Q % 4 != 0: scalar reductions; many row blocks
 def test_outer_matches_fp32(planes, M, P, Q):
     ops = _ops()
     A, B = _rand(M, P, seed=1), _rand(M, Q, seed=2)

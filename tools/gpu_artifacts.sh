@@ -14,8 +14,8 @@ timeout 400 ncu --set full --clock-control none --import-source on -k regex:line
     -o gpurun_out/${R}_prof_linear -f python tools/one_step.py 512 1 > /dev/null 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:outer_kernel -s 20 -c 3 \
     -o gpurun_out/${R}_prof_outer -f python tools/one_step.py 512 1 > /dev/null 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:attn_mma -s 4 -c 2 \
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:attn_mma -s 1 -c 2 \
     -o gpurun_out/${R}_prof_attn -f python tools/one_step.py 512 1 > /dev/null 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:ln_bwd -s 20 -c 1 \
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:ln_bwd -s 4 -c 2 \
     -o gpurun_out/${R}_prof_ln_bwd -f python tools/one_step.py 512 1 > /dev/null 2>&1
 ls -la gpurun_out/
