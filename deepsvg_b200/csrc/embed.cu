@@ -188,32 +188,69 @@ struct EmbedBwdArgs {
   Dropout drop;
 };
 
+// The ids of the block's sequences are staged in shared memory once (commands, group ids, args + 1, and per token whether
+// any argument slot is used: two thirds of the positions are EOS padding), and the dx rows are fetched eight positions at a
+// time so that eight independent row loads per thread are in flight.  (The first version walked the tokens one by one
+// with the id loads, the dx load and the reductions in one dependent chain: 380 us per launch at N = 512, latency-bound.)
 __global__ void __launch_bounds__(512) embed_bwd_kernel(EmbedBwdArgs a) {
-  extern __shared__ float sm[];  // [7 + n_grp][d]
+  extern __shared__ float sm[];  // [7 + n_grp][d] accumulators | int cmd[ntok] | int grp[ntok] | int used[ntok] | int arg[ntok][n_args]
   const int c = threadIdx.x;
-  const int d = a.d;
+  const int d = a.d, L = a.L, na = a.n_args;
   const int nsm = 7 + a.n_grp;
-  for (int r = 0; r < nsm; ++r) sm[r * d + c] = 0.f;
   const int q0 = blockIdx.x * a.spb;
   const int q1 = min(a.nseq, q0 + a.spb);
-  for (int s = 0; s < a.L; ++s) {
-    float accp = 0.f;
-    for (int q = q0; q < q1; ++q) {
-      const size_t t = size_t(q) * a.L + s;
-      const size_t idx = t * d + c;
-      float v = a.dx[idx];
-      if (a.drop.p > 0.f) v *= dropout_mult(a.drop, idx);
-      accp += v;
-      const int cmd = int(a.commands[t]);
-      sm[cmd * d + c] += v;
-      if (a.dgrp_tab != nullptr) sm[(7 + a.grp[t]) * d + c] += v;
-      const float* ar = a.args + t * a.n_args;
-      for (int k = 0; k < a.n_args; ++k) {
-        const int vv = int(ar[k]) + 1;
-        if (vv > 0) atomicAdd(a.dD + (size_t(k) * a.V + vv) * d + c, v);
+  const int nq = q1 - q0, ntok = nq * L, cap = a.spb * L;
+  int* s_cmd = reinterpret_cast<int*>(sm + size_t(nsm) * d);
+  int* s_grp = s_cmd + cap;
+  int* s_used = s_grp + cap;
+  int* s_arg = s_used + cap;
+  for (int r = 0; r < nsm; ++r) sm[r * d + c] = 0.f;
+  for (int i = c; i < ntok; i += blockDim.x) {
+    const size_t t = size_t(q0) * L + i;
+    s_cmd[i] = int(a.commands[t]);
+    s_grp[i] = a.dgrp_tab != nullptr ? int(a.grp[t]) : 0;
+    const float* ar = a.args + t * na;
+    int used = 0;
+    for (int k = 0; k < na; ++k) {
+      const int vv = int(ar[k]) + 1;   // 0 = PAD (argument value -1)
+      s_arg[i * na + k] = vv;
+      used |= (vv > 0);
+    }
+    s_used[i] = used;
+  }
+  __syncthreads();
+  constexpr int kPos = 8;
+  for (int s0 = 0; s0 < L; s0 += kPos) {
+    float accp[kPos];
+#pragma unroll
+    for (int j = 0; j < kPos; ++j) accp[j] = 0.f;
+    for (int qi = 0; qi < nq; ++qi) {
+      const size_t tbase = size_t(q0 + qi) * L + s0;
+      float v[kPos];
+#pragma unroll
+      for (int j = 0; j < kPos; ++j) v[j] = (s0 + j < L) ? __ldg(a.dx + (tbase + j) * d + c) : 0.f;
+#pragma unroll
+      for (int j = 0; j < kPos; ++j) {
+        if (s0 + j < L) {
+          float x = v[j];
+          if (a.drop.p > 0.f) x *= dropout_mult(a.drop, (tbase + j) * d + c);
+          accp[j] += x;
+          const int li = qi * L + s0 + j;
+          sm[s_cmd[li] * d + c] += x;
+          if (a.dgrp_tab != nullptr) sm[(7 + s_grp[li]) * d + c] += x;
+          if (s_used[li]) {
+            const int* ar = s_arg + li * na;
+            for (int k = 0; k < na; ++k) {
+              const int vv = ar[k];
+              if (vv > 0) atomicAdd(a.dD + (size_t(k) * a.V + vv) * d + c, x);
+            }
+          }
+        }
       }
     }
-    atomicAdd(a.dpos_tab + size_t(s) * d + c, accp);
+#pragma unroll
+    for (int j = 0; j < kPos; ++j)
+      if (s0 + j < L) atomicAdd(a.dpos_tab + size_t(s0 + j) * d + c, accp[j]);
   }
   for (int r = 0; r < 7; ++r) atomicAdd(a.dcmd_tab + size_t(r) * d + c, sm[r * d + c]);
   if (a.dgrp_tab != nullptr)
@@ -377,7 +414,8 @@ extern "C" int dsvg_embed_bwd(const float* commands, const float* args, const ui
   a.nseq = nseq; a.L = L; a.V = V; a.n_args = n_args; a.d = d; a.n_grp = d_grp_tab ? n_grp : 0;
   a.spb = 4;
   a.drop = make_dropout(drop_p, drop_site, seed);
-  const size_t smem = sizeof(float) * size_t(7 + a.n_grp) * d;
+  const size_t smem = sizeof(float) * size_t(7 + a.n_grp) * d + sizeof(int) * size_t(a.spb) * L * (3 + n_args);
+  DSVG_CHECK(smem <= 48 * 1024, "dsvg_embed_bwd: sequence too long for the id staging buffer (%zu bytes)", smem);
   embed_bwd_kernel<<<ceil_div(nseq, a.spb), d, smem, st>>>(a);
   ++g_launches;
   DSVG_LAUNCH_CHECK();

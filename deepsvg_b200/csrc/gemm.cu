@@ -485,8 +485,35 @@ constexpr uint32_t kLeanFeat[] = {
     F_BIAS | F_DROP | F_ROWVEC | F_RES | F_OUTF,  // 4: out-proj / FFN second linear into the fp32 residual stream
     F_MASK | F_OUTA,                          // 5: dgrad through ReLU (+dropout) mask
     F_ACCS | F_RES | F_OUTF,                  // 6: head dgrads accumulated in fp32
+    F_BIAS | F_OUTF,                          // 7: fp32 rows of ANY alignment (the 2827-wide logits, N = 7 / 2 heads);
+                                              //    chosen by pick_mode for ep.vec == 0, never by the feature search
 };
-constexpr int kNumLean = sizeof(kLeanFeat) / sizeof(kLeanFeat[0]);
+constexpr int kNumLean = 6;                   // modes found by the feature search in pick_mode
+
+// mode 7: one 32 x 32 chunk -> out_f32[row, col] = acc + bias[col]; lane = column, so every store instruction writes one
+// 128-byte row segment whatever the row stride (no 16-byte alignment needed).
+__device__ __forceinline__ void plain_rows_chunk(uint32_t (&v)[32], uint32_t stage_addr, int lane, long long row0, int col0,
+                                                 int M, int N, const Epi& ep) {
+  const uint32_t my = stage_addr + lane * (kStageRow * 4);
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    st_shared_v4(my + q * 16, __uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                 __uint_as_float(v[4 * q + 3]));
+  __syncwarp();
+  const int col = col0 + lane;
+  if (col < N) {
+    const float b = ep.bias != nullptr ? __ldg(ep.bias + col) : 0.f;
+    float* out = ep.out_f32 + row0 * (long long)ep.out_f32_ld + col;
+    const int rows = (M - row0) < 32 ? int(M - row0) : 32;
+    if (rows == 32) {
+#pragma unroll
+      for (int r = 0; r < 32; ++r) out[(long long)r * ep.out_f32_ld] = ld_shared_f32(stage_addr + (r * kStageRow + lane) * 4) + b;
+    } else {
+      for (int r = 0; r < rows; ++r) out[(long long)r * ep.out_f32_ld] = ld_shared_f32(stage_addr + (r * kStageRow + lane) * 4) + b;
+    }
+  }
+  __syncwarp();
+}
 
 // ------------------------------------------------------------------------------------------------
 // TMA-store epilogue (act outputs): thread = accumulator row, 32 columns straight from TMEM; every step runs in
@@ -581,7 +608,7 @@ __device__ __forceinline__ void tma_out_load_mask(uint4 (&mk)[4], long long grow
 __host__ __device__ constexpr int lin_epi_warps(int mode, int bn) {
   // the fp32-residual epilogues (modes 4, 6) are stall-bound chains of shared / global accesses with no single hot
   // spot (ncu: issue slots 29 % busy with 2 warps per scheduler): the 256-wide, one-CTA-per-SM kernel runs them 16 wide
-  return ((mode == 3 || mode == 4 || mode == 5 || mode == 6) && bn == 256) ? 16 : 8;
+  return ((mode >= 3 && mode <= 7) && bn == 256) ? 16 : 8;
 }
 // act-output lean modes write their bf16 tile through shared memory with one TMA store per 64-column box
 __host__ __device__ constexpr bool lin_tma_out(int mode) { return mode == 1 || mode == 2 || mode == 3 || mode == 5; }
@@ -764,6 +791,18 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * BN + c), v);
           tmem_ld_wait();
           epilogue_chunk<false>(v, stage_buf, lane, row0, n0 + c, M, N, ep, 1.f, nullptr, 0);
+        }
+      } else if constexpr (MODE == 7) {
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        if (warp == 2) trace_stamp(ep, it, 10, lane);
+#pragma unroll 1
+        for (int c = half * 32; c < BN; c += kCols) {
+          if (n0 + c >= N) break;
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * BN + c), v);
+          tmem_ld_wait();
+          plain_rows_chunk(v, stage_buf, lane, row0, n0 + c, M, N, ep);
         }
       } else if constexpr (lin_tma_out(MODE)) {
         // Streamed TMA-store epilogue.  A "pass" = all epilogue warps draining kCols accumulator columns into their
@@ -1130,6 +1169,7 @@ static int launch_linear_fast(const CUtensorMap& a, const CUtensorMap& b, int M,
     case 4: return launch_linear_mode<BN, 1, 4>(a, a, b, b, M, N, K, ep, st);
     case 5: return launch_linear_mode<BN, 1, 5>(a, a, b, b, M, N, K, ep, st);
     case 6: return launch_linear_mode<BN, 1, 6>(a, a, b, b, M, N, K, ep, st);
+    case 7: return launch_linear_mode<BN, 1, 7>(a, a, b, b, M, N, K, ep, st);
     default: return launch_linear_mode<BN, 1, 0>(a, a, b, b, M, N, K, ep, st);
   }
 }
@@ -1137,7 +1177,14 @@ static int launch_linear_fast(const CUtensorMap& a, const CUtensorMap& b, int M,
 // which lean epilogue (if any) covers exactly the requested steps
 static int pick_mode(const Epi& ep, bool split, int N) {
   static const bool off = [] { const char* e = getenv("DSVG_EPI"); return e && e[0] == 'g'; }();  // "generic"
-  if (off || split || ep.vec != 1 || ep.mask_lo_off != 0 || ep.out_lo_off != 0) return 0;
+  if (off || split) return 0;
+  if (ep.vec == 0) {   // unaligned rows: only the plain "acc + bias -> fp32" head epilogue has a lean version
+    static const bool no7 = [] { const char* e = getenv("DSVG_EPI"); return e && e[0] == '7'; }();  // A/B switch
+    const bool plain = ep.out_f32 && !ep.out_act && !ep.acc_scale_dev && ep.scale_cols == 0 && !ep.relu &&
+                       !(ep.drop.p > 0.f) && !ep.rowvec && !ep.mask && !ep.residual;
+    return (plain && !no7) ? 7 : 0;
+  }
+  if (ep.vec != 1 || ep.mask_lo_off != 0 || ep.out_lo_off != 0) return 0;
   uint32_t f = 0;
   if (ep.acc_scale_dev) f |= F_ACCS;
   if (ep.bias) f |= F_BIAS;

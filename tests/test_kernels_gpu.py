@@ -28,7 +28,7 @@ def _rel(a, b):
 # ------------------------------------------------------------------------------------------------ GEMMs
 @pytest.mark.parametrize("planes", [1, 2])
 @pytest.mark.parametrize("M,N,K", [(512, 256, 256), (300, 768, 256), (496, 7, 256), (992, 2827, 256), (1024, 256, 512),
-                                   (64, 256, 64)])
+                                   (64, 256, 64), (16650, 2827, 256), (16650, 7, 256)])   # last two: wide / unaligned rows
 def test_linear_matches_fp32(planes, M, N, K):
     ops = _ops()
     X, W, b = _rand(M, K, seed=1), _rand(N, K, seed=2, scale=K ** -0.5), _rand(N, seed=3)
