@@ -4,7 +4,8 @@
 //   dsvg_outer  : C[P,Q] += alpha * A[M,P]^T . B[M,Q]      both operands MN-major  (wgrad, contraction over rows)
 //
 // Both are warp-specialised: warp 0 = TMA producer (one elected lane), warp 1 = tcgen05.mma issuer (one lane) and
-// TMEM owner, warps 2..5 = epilogue (TMEM -> registers -> shared-memory transpose -> coalesced global accesses).
+// TMEM owner, warps 2.. = epilogue (8 or 16 warps: TMEM -> registers -> bf16 staging tile + bulk tensor store, or
+// shared-memory transpose + coalesced global accesses / vector reductions).
 // Operands land in shared memory through TMA with the 128-byte swizzle that the UMMA shared-memory descriptors
 // name; accumulators live in TMEM (fp32).  dsvg_linear is persistent (static round-robin tile schedule) with two
 // TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
@@ -148,7 +149,6 @@ struct Epi {
   long long* dbg;  // development trace (dsvg_debug_linear_trace): per-tile clock64 stamps of CTA 0, or null
 };
 
-constexpr int kThreads = 192;       // 6 warps
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;         // 64 bf16 = 128 bytes = one swizzle span
 constexpr int kStageRow = 36;       // fp32 staging row stride in words: 16-byte aligned rows, conflict-free v4 access
@@ -603,8 +603,7 @@ __device__ __forceinline__ void tma_out_load_mask(uint4 (&mk)[4], long long grow
 // ------------------------------------------------------------------------------------------------
 // dsvg_linear kernel
 // ------------------------------------------------------------------------------------------------
-// warp 0 TMA, warp 1 MMA, then E epilogue warps (E/4 per TMEM lane quarter).  The store-only lean epilogues (modes 1-3)
-// are latency-bound on the TMEM -> smem -> global chain and need few registers, so they run 16 warps; the others 8.
+// warp 0 TMA, warp 1 MMA, then E epilogue warps (E/4 per TMEM lane quarter).
 __host__ __device__ constexpr int lin_epi_warps(int mode, int bn) {
   // the fp32-residual epilogues (modes 4, 6) are stall-bound chains of shared / global accesses with no single hot
   // spot (ncu: issue slots 29 % busy with 2 warps per scheduler): the 256-wide, one-CTA-per-SM kernel runs them 16 wide
@@ -768,7 +767,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       }
     }
   } else {
-    // =================== epilogue warps (2..9) ===================
+    // =================== epilogue warps (2 .. 2 + kEpiWarps) ===================
     const int quarter = warp & 3;         // TMEM lane quarter this warp may read
     const int half = (warp - 2) >> 2;     // which 32-column chunk of every kCols-wide pass this warp drains
     const uint32_t stage_buf = smem_u32(staging) + (warp - 2) * kStageWarpBytes;
