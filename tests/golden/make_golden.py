@@ -60,7 +60,40 @@ CASES = {
                                          n_layers_decode=1, max_num_groups=4, max_total_len=12, args_dim=15,
                                          use_vae=True, label_condition=True, n_labels=5, dim_label=8), 3, True),
     "hier_cfg1": ("hierarchical", dict(use_vae=False), 2, False),   # BASELINE.json configs[0]
+    # hand-built edge cases (see edge_batch): one-command path, empty paths, paths filled to max_seq_len (no EOS inside
+    # the window), the 'a' and 'z' commands, argument values 0 and args_dim - 1
+    "edge_hier": ("hierarchical", dict(d_model=32, n_heads=4, dim_feedforward=64, dim_z=24, n_layers=2,
+                                       n_layers_decode=2, max_num_groups=3, max_seq_len=6, args_dim=15,
+                                       use_vae=False), 4, True),
 }
+
+
+def edge_batch(cfg):
+    """4 icons x 3 paths x (6 + 2) positions.  Commands: m=0 l=1 c=2 a=3 EOS=4 SOS=5 z=6 (difflib/tensor.py:10-21)."""
+    M_, L_, C_, A_, Z_ = O.CMD_M, O.CMD_L, O.CMD_C, 3, 6
+    paths = [
+        [[M_], [], []],                                            # a one-command path, two empty (invisible) paths
+        [[M_, L_, C_, A_, Z_, L_], [M_, C_, C_, C_, C_, C_], [M_, A_, L_, Z_, M_, L_]],   # every path at max_seq_len
+        [[M_, Z_], [M_, A_, A_, C_], []],
+        [[M_, C_, C_, C_, C_, C_], [M_, L_], [M_, L_, L_]],
+    ]
+    G, S = cfg.max_num_groups, cfg.max_seq_len
+    cmd = torch.full((len(paths), G, S + 2), float(O.CMD_EOS))
+    arg = torch.full((len(paths), G, S + 2, cfg.n_args), -1.0)
+    g = torch.Generator().manual_seed(31)
+    for i, icon in enumerate(paths):
+        for p, body in enumerate(icon):
+            cmd[i, p, 0] = O.CMD_SOS
+            if not body:
+                continue
+            b = torch.tensor(body)
+            cmd[i, p, 1:1 + len(body)] = b.float()
+            vals = torch.randint(0, cfg.args_dim, (len(body), cfg.n_args), generator=g).float()
+            vals[0, :] = 0.0                       # smallest argument value
+            vals[-1, :] = float(cfg.args_dim - 1)   # largest
+            m = O.CMD_ARGS_MASK[b].float()
+            arg[i, p, 1:1 + len(body)] = vals * m - (1 - m)
+    return cmd, arg
 WEIGHTS = dict(O.DEFAULT_WEIGHTS)
 
 
@@ -97,7 +130,8 @@ def run_case(name):
     model.load_state_dict(params, strict=False)
     model.eval()
     loss_fn = SVGLoss(cfg_r)
-    cmd, arg = O.synth_batch(cfg_o, batch, seed=99)
+    cmd, arg = edge_batch(cfg_o) if name.startswith("edge") else O.synth_batch(cfg_o, batch, seed=99)
+    assert cmd.shape[0] == batch
     cmd, arg = cmd.double(), arg.double()
     label = None
     kw = {}

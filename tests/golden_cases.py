@@ -19,6 +19,10 @@ CASES = {
                                          n_layers_decode=1, max_num_groups=4, max_total_len=12, args_dim=15,
                                          use_vae=True, label_condition=True, n_labels=5, dim_label=8), True),
     "hier_cfg1": ("hierarchical", dict(use_vae=False), False),
+    # hand-built edge cases: one-command path, empty paths, paths filled to max_seq_len, 'a' / 'z' commands, extreme arg values
+    "edge_hier": ("hierarchical", dict(d_model=32, n_heads=4, dim_feedforward=64, dim_z=24, n_layers=2,
+                                       n_layers_decode=2, max_num_groups=3, max_seq_len=6, args_dim=15,
+                                       use_vae=False), True),
 }
 
 
