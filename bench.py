@@ -157,7 +157,7 @@ def run_reference(a):
     threads = host_threads()
     # bounded sample: probe one small step, then size the per-step batch so that W + K steps take about two minutes
     _, t_probe = cpu_port_rate(4, 1, 0, threads)
-    budget_s = 120.0
+    budget_s = float(os.environ.get("DSVG_REF_BUDGET_S", "120"))   # wall-clock target for the W + K CPU steps
     per_icon = t_probe / 4.0
     batch = int(max(2, min(64, budget_s / (max(1, a.steps + a.warmup) * per_icon))))
     a.cpu_batch = batch
