@@ -65,19 +65,25 @@ CASES = {
     "edge_hier": ("hierarchical", dict(d_model=32, n_heads=4, dim_feedforward=64, dim_z=24, n_layers=2,
                                        n_layers_decode=2, max_num_groups=3, max_seq_len=6, args_dim=15,
                                        use_vae=False), 4, True),
+    # the same edge batch at a configuration the CUDA path supports (head_dim 32), for the GPU parity test
+    "edge_d128": ("hierarchical", dict(use_vae=False, d_model=128, n_heads=4, dim_feedforward=256, dim_z=64, n_layers=2,
+                                       n_layers_decode=2, max_num_groups=4, max_seq_len=10), 4, False),
 }
 
 
 def edge_batch(cfg):
-    """4 icons x 3 paths x (6 + 2) positions.  Commands: m=0 l=1 c=2 a=3 EOS=4 SOS=5 z=6 (difflib/tensor.py:10-21)."""
+    """4 icons x G paths x (S + 2) positions.  Commands: m=0 l=1 c=2 a=3 EOS=4 SOS=5 z=6 (difflib/tensor.py:10-21)."""
     M_, L_, C_, A_, Z_ = O.CMD_M, O.CMD_L, O.CMD_C, 3, 6
-    paths = [
-        [[M_], [], []],                                            # a one-command path, two empty (invisible) paths
-        [[M_, L_, C_, A_, Z_, L_], [M_, C_, C_, C_, C_, C_], [M_, A_, L_, Z_, M_, L_]],   # every path at max_seq_len
-        [[M_, Z_], [M_, A_, A_, C_], []],
-        [[M_, C_, C_, C_, C_, C_], [M_, L_], [M_, L_, L_]],
-    ]
     G, S = cfg.max_num_groups, cfg.max_seq_len
+    cyc = [L_, C_, A_, Z_, L_, M_, C_, A_]
+    full = lambda k: [M_] + [cyc[(j + k) % len(cyc)] for j in range(S - 1)]      # a path filled to max_seq_len
+    pad = lambda icon: icon + [[] for _ in range(G - len(icon))]
+    paths = [
+        pad([[M_]]),                                               # a one-command path, the others empty (invisible)
+        [full(p) for p in range(G)],                               # every path at max_seq_len (no EOS inside the window)
+        pad([[M_, Z_], [M_, A_, A_, C_]]),
+        pad([[M_] + [C_] * (S - 1), [M_, L_], [M_, L_, L_]]),
+    ]
     cmd = torch.full((len(paths), G, S + 2), float(O.CMD_EOS))
     arg = torch.full((len(paths), G, S + 2, cfg.n_args), -1.0)
     g = torch.Generator().manual_seed(31)

@@ -23,6 +23,8 @@ CASES = {
     "edge_hier": ("hierarchical", dict(d_model=32, n_heads=4, dim_feedforward=64, dim_z=24, n_layers=2,
                                        n_layers_decode=2, max_num_groups=3, max_seq_len=6, args_dim=15,
                                        use_vae=False), True),
+    "edge_d128": ("hierarchical", dict(use_vae=False, d_model=128, n_heads=4, dim_feedforward=256, dim_z=64, n_layers=2,
+                                       n_layers_decode=2, max_num_groups=4, max_seq_len=10), False),
 }
 
 

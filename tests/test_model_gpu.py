@@ -212,3 +212,24 @@ def test_greedy_sample_matches_oracle_decoding():
     c1, a1 = model.greedy_sample(c[:1], a[:1], None, None)
     k1, _ = model.greedy_sample(c[:1], a[:1], None, None, concat_groups=False)
     assert c1.shape[0] == 1 and c1.shape[1] == int(((k1 == 4).cumsum(-1) == 0).sum()) and a1.shape[1:] == (c1.shape[1], 11)
+
+
+@pytest.mark.xfail(strict=False, reason="added after the round's GPU minutes were spent: not yet run on a GPU (an XPASS "
+                                        "confirms it; see DESIGN.md section 8)")
+def test_parity_mode_on_edge_inputs_matches_reference_golden():
+    """One-command / empty / max-length paths, the 'a' and 'z' commands, extreme argument values -- against numbers
+    produced by the reference itself (tests/golden/make_golden.py: edge_d128)."""
+    cfg, fx, _ = load_case("edge_d128")
+    model, loss_fn, _ = _build(cfg, "bf16x3", seed=int(fx["seed_params"]))
+    cmd, arg = torch.from_numpy(fx["commands"]), torch.from_numpy(fx["args"])
+    out, ls, grads = _run(model, loss_fn, cmd, arg)
+    idx = lambda t, n: t.reshape(-1)[torch.linspace(0, t.numel() - 1, n).long()]
+    for k in ("command_logits", "args_logits", "visibility_logits"):
+        assert tuple(out[k].shape) == tuple(fx["O_shape_" + k]), k
+        got = idx(out[k].detach().cpu(), 4096) if out[k].numel() > 4096 else out[k].detach().cpu().reshape(-1)
+        np.testing.assert_allclose(got.numpy(), fx["O_" + k].reshape(-1), rtol=1e-3, atol=1e-4, err_msg=k)
+    for k in ("loss", "loss_cmd", "loss_args", "loss_visibility"):
+        assert abs(ls[k].item() - float(fx["L_" + k])) <= 1e-3 * float(fx["L_" + k]), k
+    for k, g in grads.items():
+        ref_norm = float(fx["Gnorm_" + k])
+        assert abs(g.double().norm().item() - ref_norm) <= 1e-2 * ref_norm + 1e-9, k
