@@ -60,6 +60,28 @@ def peaks():
     return 1400.0, 1590.0, 6650.0, "fallback"
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel family, averaged over the launches of
+    the committed `ncu --set full` capture (profiles/r*_ncu_linear.txt, written by tools/summarize_profiles.py)."""
+    try:
+        import glob
+        files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_linear.txt")))
+        tot, n = 0.0, 0
+        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for line in open(files[-1]):
+            if not line.startswith("{"):
+                continue
+            d = json.loads(line)
+            b = 0.0
+            for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                v, u = d[k].split()
+                b += float(v) * unit[u]
+            tot, n = tot + b, n + 1
+        return (tot / n, "%s: mean over %d captured linear_kernel launches" % (os.path.basename(files[-1]), n)) if n else (None, None)
+    except Exception:
+        return None, None
+
+
 class ClockSampler(threading.Thread):
     """SM clock and throttle reasons DURING the timed region, via in-process NVML (spawning nvidia-smi every 100 ms was
     measured to stall CUDA launches for 100-250 ms at a time on a multi-GPU box)."""
@@ -362,7 +384,7 @@ def run_ours(a):
         "roofline": {"bound": "tensor", "kernel": "dsvg::linear_kernel (tcgen05 X.W^T, all forward + dgrad GEMMs)",
                      "achieved": lin_tflops, "peak": sus, "unit": "TFLOP/s", "frac": lin_tflops / sus if sus else None,
                      "peak_source": src + " (bf16_tflops_sustained)", "launches_per_step": lin[0],
-                     "ms_per_step_in_kernel": lin[2], "traffic": None,
+                     "ms_per_step_in_kernel": lin[2], "traffic": ncu_traffic()[0], "traffic_source": ncu_traffic()[1],
                      "step": {"achieved": step_tflops, "frac": step_tflops / sus, "gflop_per_icon": TRAIN_GFLOP_PER_ICON},
                      "families": {k: {"launches": v[0], "ms": v[2], "tflops": (v[1] / (v[2] / 1e3) / 1e12 if v[2] else 0)}
                                   for k, v in fam.items()},
