@@ -177,12 +177,19 @@ def run_case(name):
     for k, g in grads.items():
         fx["Gnorm_" + k] = np.float64(g.double().norm().item())
         fx["G_" + k] = (g if full else sample(g, 512)).detach().numpy()
-    path = os.path.join(HERE, name + ".npz")
+    path = os.path.join(OUT_DIR, name + ".npz")
     np.savez_compressed(path, **fx)
     print(name, {k: float(v) for k, v in fx.items() if k.startswith("L_")}, os.path.getsize(path) // 1024, "KB")
 
 
+OUT_DIR = HERE
+
 if __name__ == "__main__":
     torch.manual_seed(0)
-    for n in (sys.argv[1:] or CASES):
+    argv = sys.argv[1:]
+    if "--out" in argv:                      # tests/test_oracle_golden.py regenerates into a scratch directory
+        OUT_DIR = argv[argv.index("--out") + 1]
+        del argv[argv.index("--out"):argv.index("--out") + 2]
+        os.makedirs(OUT_DIR, exist_ok=True)
+    for n in (argv or CASES):
         run_case(n)

@@ -83,3 +83,24 @@ def test_matmul_modes_are_close():
     b1 = O.forward(params, cfg, cmd, arg, matmul="bf16")["args_logits"]
     e3, e1 = (x3 - ref).abs().max().item(), (b1 - ref).abs().max().item()
     assert e3 < 2e-4 and e3 < e1 / 20, (e3, e1)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/deepsvg"), reason="the reference checkout exists only in the authoring container")
+def test_fixtures_regenerate_from_the_reference(tmp_path):
+    """Re-executes the reference (tests/golden/make_golden.py) and requires the committed fixtures to come out again
+    (inputs bit for bit; fp64 results to 1e-10 relative, so a different BLAS thread split cannot make it flaky)."""
+    import subprocess
+    import sys
+    names = ["tiny_hier", "edge_hier"]
+    r = subprocess.run([sys.executable, os.path.join(HERE, "golden", "make_golden.py"), "--out", str(tmp_path)] + names,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    for n in names:
+        new = dict(np.load(os.path.join(str(tmp_path), n + ".npz"), allow_pickle=False))
+        old = dict(np.load(os.path.join(HERE, "golden", n + ".npz"), allow_pickle=False))
+        assert sorted(new) == sorted(old), n
+        for k in old:
+            if old[k].dtype.kind == "f" and not k.startswith(("commands", "args")):
+                np.testing.assert_allclose(new[k], old[k], rtol=1e-10, atol=1e-13, err_msg="%s/%s" % (n, k))
+            else:
+                assert np.array_equal(new[k], old[k]), (n, k)
