@@ -12,6 +12,9 @@ U32 = C.c_uint32
 U64 = C.c_uint64
 DROP = [F, U32, U64]
 
+#: must equal dsvg_abi_version() of the loaded library (checked in _lib.load())
+ABI_VERSION = 2
+
 SIGNATURES = {
     "dsvg_abi_version": (I, []),
     "dsvg_linear": (I, [P, Z, I, P, Z, I, I, I, I, P, P]),

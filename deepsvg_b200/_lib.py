@@ -5,6 +5,7 @@ Loading the library itself needs no GPU (the CPU test-suite checks the exported 
 """
 import ctypes as C
 import os
+import sys
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
@@ -52,13 +53,25 @@ def load():
     if os.environ.get("DSVG_NO_BUILD", "0") != "1":
         try:
             from .csrc.build import build
-            build()
-        except Exception as e:  # building is best-effort; loading below is not
+            build()          # takes a file lock: under torchrun every rank calls this, one of them compiles
+        except Exception as e:
             if not _LIB_PATH.exists():
                 raise RuntimeError(f"libdsvg_b200.so is missing and could not be built: {e}") from e
+            # a library exists but the rebuild failed: it may predate the sources -- the ABI check below is the gate
+            sys.stderr.write(f"deepsvg_b200: WARNING: rebuilding libdsvg_b200.so failed ({e}); "
+                             "loading the existing (possibly stale) library\n")
     if not _LIB_PATH.exists():
         raise RuntimeError(f"{_LIB_PATH} not found: run `python -m deepsvg_b200.csrc.build` (no CPU fallback exists)")
     lib = C.CDLL(str(_LIB_PATH))
+    from ._abi import ABI_VERSION
+    try:
+        lib.dsvg_abi_version.restype = C.c_int
+        have = int(lib.dsvg_abi_version())
+    except AttributeError:
+        have = -1
+    if have != ABI_VERSION:
+        raise RuntimeError(f"{_LIB_PATH} exports ABI version {have}, the Python binding expects {ABI_VERSION}: rebuild "
+                           "with `python -m deepsvg_b200.csrc.build --force`")
     lib.dsvg_last_error.restype = C.c_char_p
     lib.dsvg_launch_count.restype = C.c_ulonglong
     _declare(lib)

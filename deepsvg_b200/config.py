@@ -81,3 +81,13 @@ def check_supported(cfg):
         raise NotImplementedError("deepsvg_b200: n_args=11 / n_commands=7 are fixed by the SVG token vocabulary")
     if cfg.args_dim + 1 > 288:
         raise NotImplementedError("deepsvg_b200: args_dim must be <= 287")
+    # sequence lengths the attention kernels hold on chip (csrc/attention.cu: the backward keeps Q, K, V, dO and two
+    # L x L tiles of one (sequence, head) pair in shared memory; csrc/attention_mma.cu: L <= 80 on the tensor-core path)
+    two = cfg.encode_stages == 2
+    longest = (cfg.max_seq_len if two else cfg.max_total_len) + 2
+    if two:
+        longest = max(longest, cfg.max_num_groups, cfg.num_groups_proposal)
+    if 4 * (4 * longest * hd + 2 * longest * (longest | 1) + 3) > 227 * 1024:
+        raise NotImplementedError("deepsvg_b200: sequences of %d positions (head_dim %d) exceed the attention kernels' "
+                                  "shared-memory tile (limits: 153 / 139 / 115 tokens for head_dim 16 / 32 / 64)"
+                                  % (longest, hd))

@@ -253,9 +253,18 @@ int dsvg_attn_mma_fwd(const bf16* qkv, const uint8_t* valid, bf16* out, int nseq
                       cudaStream_t st);
 int dsvg_attn_mma_bwd(const bf16* qkv, const uint8_t* valid, const bf16* dout, bf16* dqkv, int nseq, int L, int H,
                       float q_scale, Dropout drop, cudaStream_t st);
-static bool use_mma(bool single_plane, int L, int head_dim) {
+int dsvg_attn_gmma(bool bwd, const bf16* qkv, const uint8_t* valid, bf16* out, const bf16* dout, bf16* dqkv, int nseq, int L,
+                   int H, int head_dim, float q_scale, Dropout drop, cudaStream_t st);
+static bool attn_simt_forced() {
   static const bool off = [] { const char* e = getenv("DSVG_ATTN"); return e && e[0] == 's'; }();  // "simt"
-  return !off && single_plane && head_dim == 32 && L <= 32;
+  return off;
+}
+static bool use_mma(bool single_plane, int L, int head_dim) {
+  return !attn_simt_forced() && single_plane && head_dim == 32 && L <= 32;
+}
+// general tensor-core kernel (attention_mma.cu): every other fast-mode shape of the BASELINE configs
+static bool use_gmma(bool single_plane, int L, int head_dim) {
+  return !attn_simt_forced() && single_plane && (head_dim == 32 || head_dim == 64) && L <= 80;
 }
 
 extern "C" int dsvg_attn_fwd(const dsvg_bf16* qkv, size_t qkv_lo_off, const uint8_t* key_valid, dsvg_bf16* out,
@@ -270,6 +279,8 @@ extern "C" int dsvg_attn_fwd(const dsvg_bf16* qkv, size_t qkv_lo_off, const uint
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (use_mma(qkv_lo_off == 0 && out_lo_off == 0, L, head_dim))
     return dsvg_attn_mma_fwd(a.qkv, key_valid, a.out, nseq, L, H, a.drop, st);
+  if (use_gmma(qkv_lo_off == 0 && out_lo_off == 0, L, head_dim))
+    return dsvg_attn_gmma(false, a.qkv, key_valid, a.out, nullptr, nullptr, nseq, L, H, head_dim, 1.f, a.drop, st);
   if (head_dim == 32) return launch_attn<32>(false, a, st);
   if (head_dim == 64) return launch_attn<64>(false, a, st);
   if (head_dim == 16) return launch_attn<16>(false, a, st);
@@ -290,6 +301,8 @@ extern "C" int dsvg_attn_bwd(const dsvg_bf16* qkv, size_t qkv_lo_off, const uint
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (use_mma(qkv_lo_off == 0 && dout_lo_off == 0 && dqkv_lo_off == 0, L, head_dim))
     return dsvg_attn_mma_bwd(a.qkv, key_valid, a.dout, a.dqkv, nseq, L, H, q_scale, a.drop, st);
+  if (use_gmma(qkv_lo_off == 0 && dout_lo_off == 0 && dqkv_lo_off == 0, L, head_dim))
+    return dsvg_attn_gmma(true, a.qkv, key_valid, nullptr, a.dout, a.dqkv, nseq, L, H, head_dim, q_scale, a.drop, st);
   if (head_dim == 32) return launch_attn<32>(true, a, st);
   if (head_dim == 64) return launch_attn<64>(true, a, st);
   if (head_dim == 16) return launch_attn<16>(true, a, st);

@@ -412,3 +412,377 @@ int dsvg_attn_mma_bwd(const bf16* qkv, const uint8_t* valid, const bf16* dout, b
   ++g_launches;
   return 0;
 }
+
+// ================================================================================================================
+// General tensor-core path: head_dim 32 / 64, sequences of up to 80 positions (one-stage fonts: L = 52 / 51; scaled
+// hierarchical: L = 66 / 65 path-level, 16 group-level).  One CTA owns one (sequence, head) pair at a time; warp w owns
+// the 16-row query tile w of the LP = 16 * NT padded positions (and, in the backward, the 16-row key tile w of dK / dV).
+// Q, K, V (and dO) of the pair are staged once in shared memory; the LP x LP probability / dS tiles of the backward go
+// through shared memory as bf16 so that every product is an mma.sync m16n8k16 with ldmatrix-fed operands.
+//   reference: functional.py:168-248 (same arithmetic as the 32 x 32 kernel above).
+// ================================================================================================================
+namespace dsvg {
+
+// fragment loaders on a row-major bf16 tile with `st` elements between rows (st * 2 bytes = odd multiple of 16)
+__device__ __forceinline__ void g_load_a(uint32_t (&a)[4], uint32_t tile, int row0, int k0, int st, int lane) {
+  const int m = lane >> 3, r = lane & 7;
+  ldsm_x4(a, tile + ((row0 + (m & 1) * 8 + r) * st + k0 + (m >> 1) * 8) * 2);
+}
+__device__ __forceinline__ void g_load_a_t(uint32_t (&a)[4], uint32_t tile, int m0, int k0, int st, int lane) {
+  const int m = lane >> 3, r = lane & 7;
+  ldsm_x4_t(a, tile + ((k0 + (m >> 1) * 8 + r) * st + m0 + (m & 1) * 8) * 2);
+}
+__device__ __forceinline__ void g_load_b_nk(uint32_t (&b)[4], uint32_t tile, int n0, int k0, int st, int lane) {
+  const int m = lane >> 3, r = lane & 7;
+  ldsm_x4(b, tile + ((n0 + (m >> 1) * 8 + r) * st + k0 + (m & 1) * 8) * 2);
+}
+__device__ __forceinline__ void g_load_b_kn(uint32_t (&b)[4], uint32_t tile, int n0, int k0, int st, int lane) {
+  const int m = lane >> 3, r = lane & 7;
+  ldsm_x4_t(b, tile + ((k0 + (m & 1) * 8 + r) * st + n0 + (m >> 1) * 8) * 2);
+}
+
+template <int HD, int NT>
+struct GAttn {
+  static constexpr int LP = 16 * NT;
+  static constexpr int SH = HD + 8;        // row stride of the [LP x HD] tiles
+  static constexpr int SP = LP + 8;        // row stride of the [LP x LP] tiles
+  static constexpr int kThreads = 32 * NT;
+  static constexpr int kTileH = LP * SH;   // elements
+  static constexpr int kTileP = LP * SP;
+  static constexpr int kSmemFwd = 3 * kTileH * 2 + LP;
+  static constexpr int kSmemBwd = 4 * kTileH * 2 + 2 * kTileP * 2 + LP;
+};
+
+template <int HD, int NT>
+__device__ __forceinline__ void g_stage(bf16* dst, const bf16* src, int ld, int L) {
+  using G = GAttn<HD, NT>;
+  constexpr int kParts = HD / 8;
+  for (int chunk = threadIdx.x; chunk < G::LP * kParts; chunk += G::kThreads) {
+    const int row = chunk / kParts, part = chunk % kParts;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (row < L) v = *reinterpret_cast<const uint4*>(src + size_t(row) * ld + part * 8);
+    *reinterpret_cast<uint4*>(dst + row * G::SH + part * 8) = v;
+  }
+}
+
+// S[16 x LP] = X_w . Y^T with X rows [16 w, +16) of `x_tile`, Y = `y_tile` (both [LP x HD], row-major)
+template <int HD, int NT>
+__device__ __forceinline__ void g_scores(float (&s)[2 * NT][4], uint32_t x_tile, uint32_t y_tile, int w, int lane) {
+  using G = GAttn<HD, NT>;
+#pragma unroll
+  for (int nt = 0; nt < 2 * NT; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) s[nt][e] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < HD / 16; ++ks) {
+    uint32_t a[4];
+    g_load_a(a, x_tile, 16 * w, 16 * ks, G::SH, lane);
+#pragma unroll
+    for (int np = 0; np < NT; ++np) {
+      uint32_t b[4];
+      g_load_b_nk(b, y_tile, 16 * np, 16 * ks, G::SH, lane);
+      mma_bf16(s[2 * np], a, b[0], b[1]);
+      mma_bf16(s[2 * np + 1], a, b[2], b[3]);
+    }
+  }
+}
+
+// this thread's key columns: bit (2 nt + e) <-> column 8 nt + 2 t + e
+template <int NT>
+__device__ __forceinline__ uint32_t g_my_keys(const uint8_t* kv_sm, int t) {
+  uint32_t bits = 0;
+#pragma unroll
+  for (int nt = 0; nt < 2 * NT; ++nt)
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+      if (kv_sm[8 * nt + 2 * t + e]) bits |= 1u << (2 * nt + e);
+  return bits;
+}
+
+template <int NT>
+__device__ __forceinline__ void g_softmax(float (&s)[2 * NT][4], uint32_t keys) {
+#pragma unroll
+  for (int hrow = 0; hrow < 2; ++hrow) {
+    float m = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 2 * NT; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        float& x = s[nt][2 * hrow + e];
+        if (!((keys >> (2 * nt + e)) & 1u)) x = -INFINITY;
+        m = fmaxf(m, x);
+      }
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+    float sum = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 2 * NT; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        float& x = s[nt][2 * hrow + e];
+        x = __expf(x - m);
+        sum += x;
+      }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int nt = 0; nt < 2 * NT; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) s[nt][2 * hrow + e] *= inv;
+  }
+}
+
+// dropout multipliers of this thread's elements: one quad (4 draws) per (pair, row, key-tile pair np, t)
+template <int NT>
+__device__ __forceinline__ void g_dropout(float (&mult)[2 * NT][4], const Dropout& d, unsigned long long pair, int w, int g,
+                                          int t) {
+  constexpr int LP = 16 * NT;
+#pragma unroll
+  for (int hrow = 0; hrow < 2; ++hrow) {
+    const int i = 16 * w + g + 8 * hrow;
+    const unsigned long long q_row = ((pair * LP + i) * NT) * 4ull;
+#pragma unroll
+    for (int np = 0; np < NT; ++np) {
+      const unsigned long long quad = q_row + (unsigned long long)(np * 4 + t);
+      const uint32_t s1 = drop_stage1(uint32_t(quad), drop_hikey(d, quad));
+      const uint32_t a = drop_fin_a(s1), b = drop_fin_b(s1);
+      mult[2 * np][2 * hrow] = drop_keep_lo(a, d.thr16) ? d.scale : 0.f;
+      mult[2 * np][2 * hrow + 1] = drop_keep_hi(a, d.thr16) ? d.scale : 0.f;
+      mult[2 * np + 1][2 * hrow] = drop_keep_lo(b, d.thr16) ? d.scale : 0.f;
+      mult[2 * np + 1][2 * hrow + 1] = drop_keep_hi(b, d.thr16) ? d.scale : 0.f;
+    }
+  }
+}
+
+// out[16 x HD] = A(regs: 16 x LP in C-fragment layout) . Y,  Y = [LP x HD] row-major tile
+template <int HD, int NT>
+__device__ __forceinline__ void g_mul_regs(float (&o)[HD / 8][4], const float (&p)[2 * NT][4], uint32_t y_tile, int lane) {
+  using G = GAttn<HD, NT>;
+#pragma unroll
+  for (int nt = 0; nt < HD / 8; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[nt][e] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < NT; ++ks) {
+    uint32_t a[4];
+    a[0] = pack_bf16(p[2 * ks][0], p[2 * ks][1]);
+    a[1] = pack_bf16(p[2 * ks][2], p[2 * ks][3]);
+    a[2] = pack_bf16(p[2 * ks + 1][0], p[2 * ks + 1][1]);
+    a[3] = pack_bf16(p[2 * ks + 1][2], p[2 * ks + 1][3]);
+#pragma unroll
+    for (int np = 0; np < HD / 16; ++np) {
+      uint32_t b[4];
+      g_load_b_kn(b, y_tile, 16 * np, 16 * ks, G::SH, lane);
+      mma_bf16(o[2 * np], a, b[0], b[1]);
+      mma_bf16(o[2 * np + 1], a, b[2], b[3]);
+    }
+  }
+}
+// out[16 x HD] (rows = key tile w) = Z^T . Y with Z = [LP(query) x LP(key)] tile (stride SP), Y = [LP(query) x HD] tile
+template <int HD, int NT>
+__device__ __forceinline__ void g_mul_t(float (&o)[HD / 8][4], uint32_t z_tile, uint32_t y_tile, int w, int lane) {
+  using G = GAttn<HD, NT>;
+#pragma unroll
+  for (int nt = 0; nt < HD / 8; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[nt][e] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < NT; ++ks) {
+    uint32_t a[4];
+    g_load_a_t(a, z_tile, 16 * w, 16 * ks, G::SP, lane);
+#pragma unroll
+    for (int np = 0; np < HD / 16; ++np) {
+      uint32_t b[4];
+      g_load_b_kn(b, y_tile, 16 * np, 16 * ks, G::SH, lane);
+      mma_bf16(o[2 * np], a, b[0], b[1]);
+      mma_bf16(o[2 * np + 1], a, b[2], b[3]);
+    }
+  }
+}
+template <int HD>
+__device__ __forceinline__ void g_store_global(bf16* dst, int ld, int L, int row0, const float (&c)[HD / 8][4], float mul,
+                                               int g, int t) {
+#pragma unroll
+  for (int hrow = 0; hrow < 2; ++hrow) {
+    const int i = row0 + g + 8 * hrow;
+    if (i < L) {
+#pragma unroll
+      for (int nt = 0; nt < HD / 8; ++nt)
+        *reinterpret_cast<uint32_t*>(dst + size_t(i) * ld + 8 * nt + 2 * t) =
+            pack_bf16(c[nt][2 * hrow] * mul, c[nt][2 * hrow + 1] * mul);
+    }
+  }
+}
+template <int NT>
+__device__ __forceinline__ void g_store_rows_smem(bf16* tile, int st, int row0, const float (&c)[2 * NT][4], int g, int t) {
+#pragma unroll
+  for (int hrow = 0; hrow < 2; ++hrow) {
+    const int i = row0 + g + 8 * hrow;
+#pragma unroll
+    for (int nt = 0; nt < 2 * NT; ++nt)
+      *reinterpret_cast<uint32_t*>(tile + i * st + 8 * nt + 2 * t) = pack_bf16(c[nt][2 * hrow], c[nt][2 * hrow + 1]);
+  }
+}
+
+template <int HD, int NT>
+__global__ void __launch_bounds__(32 * NT) attn_gmma_fwd_kernel(MmaAttnArgs a) {
+  using G = GAttn<HD, NT>;
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ __align__(16) bf16 sm_dyn[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int L = a.L, d = a.H * HD, ld = 3 * d;
+  bf16* Qs = sm_dyn;
+  bf16* Ks = Qs + G::kTileH;
+  bf16* Vs = Ks + G::kTileH;
+  uint8_t* kv = reinterpret_cast<uint8_t*>(Vs + G::kTileH);
+  const uint32_t q_t = smem_addr(Qs), k_t = smem_addr(Ks), v_t = smem_addr(Vs);
+  const long long npairs = (long long)a.nseq * a.H;
+  for (long long pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+    const int seq = int(pair / a.H), h = int(pair % a.H);
+    const size_t row0 = size_t(seq) * L;
+    const bf16* base = a.qkv + row0 * ld + h * HD;
+    g_stage<HD, NT>(Qs, base, ld, L);
+    g_stage<HD, NT>(Ks, base + d, ld, L);
+    g_stage<HD, NT>(Vs, base + 2 * d, ld, L);
+    for (int j = threadIdx.x; j < G::LP; j += G::kThreads) kv[j] = (j < L && (a.valid == nullptr || a.valid[row0 + j] != 0)) ? 1 : 0;
+    __syncthreads();
+    float s[2 * NT][4];
+    g_scores<HD, NT>(s, q_t, k_t, w, lane);
+    g_softmax<NT>(s, g_my_keys<NT>(kv, t));
+    if (a.drop.p > 0.f) {
+      float mult[2 * NT][4];
+      g_dropout<NT>(mult, a.drop, (unsigned long long)pair, w, g, t);
+#pragma unroll
+      for (int nt = 0; nt < 2 * NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s[nt][e] *= mult[nt][e];
+    }
+    float o[HD / 8][4];
+    g_mul_regs<HD, NT>(o, s, v_t, lane);
+    g_store_global<HD>(a.out + row0 * d + h * HD, d, L, 16 * w, o, 1.f, g, t);
+    __syncthreads();
+  }
+}
+
+template <int HD, int NT>
+__global__ void __launch_bounds__(32 * NT) attn_gmma_bwd_kernel(MmaAttnArgs a) {
+  using G = GAttn<HD, NT>;
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ __align__(16) bf16 sm_dyn[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int L = a.L, d = a.H * HD, ld = 3 * d;
+  bf16* Qs = sm_dyn;
+  bf16* Ks = Qs + G::kTileH;
+  bf16* Vs = Ks + G::kTileH;
+  bf16* Gs = Vs + G::kTileH;   // dO
+  bf16* Ps = Gs + G::kTileH;   // dropout-scaled probabilities  [query][key]
+  bf16* Ds = Ps + G::kTileP;   // dS                            [query][key]
+  uint8_t* kv = reinterpret_cast<uint8_t*>(Ds + G::kTileP);
+  const uint32_t q_t = smem_addr(Qs), k_t = smem_addr(Ks), v_t = smem_addr(Vs), g_t = smem_addr(Gs), p_t = smem_addr(Ps),
+                 d_t = smem_addr(Ds);
+  const long long npairs = (long long)a.nseq * a.H;
+  for (long long pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+    const int seq = int(pair / a.H), h = int(pair % a.H);
+    const size_t row0 = size_t(seq) * L;
+    const bf16* base = a.qkv + row0 * ld + h * HD;
+    g_stage<HD, NT>(Qs, base, ld, L);
+    g_stage<HD, NT>(Ks, base + d, ld, L);
+    g_stage<HD, NT>(Vs, base + 2 * d, ld, L);
+    g_stage<HD, NT>(Gs, a.dout + row0 * d + h * HD, d, L);
+    for (int j = threadIdx.x; j < G::LP; j += G::kThreads) kv[j] = (j < L && (a.valid == nullptr || a.valid[row0 + j] != 0)) ? 1 : 0;
+    __syncthreads();
+    float p[2 * NT][4], dp[2 * NT][4];
+    g_scores<HD, NT>(p, q_t, k_t, w, lane);
+    g_softmax<NT>(p, g_my_keys<NT>(kv, t));
+    g_scores<HD, NT>(dp, g_t, v_t, w, lane);          // dP = dO . V^T
+    if (a.drop.p > 0.f) {
+      float mult[2 * NT][4];
+      g_dropout<NT>(mult, a.drop, (unsigned long long)pair, w, g, t);
+#pragma unroll
+      for (int nt = 0; nt < 2 * NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          dp[nt][e] *= mult[nt][e];
+          mult[nt][e] *= p[nt][e];
+        }
+      g_store_rows_smem<NT>(Ps, G::SP, 16 * w, mult, g, t);
+    } else {
+      g_store_rows_smem<NT>(Ps, G::SP, 16 * w, p, g, t);
+    }
+#pragma unroll
+    for (int hrow = 0; hrow < 2; ++hrow) {
+      float delta = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 2 * NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) delta = fmaf(dp[nt][2 * hrow + e], p[nt][2 * hrow + e], delta);
+      delta += __shfl_xor_sync(0xffffffffu, delta, 1);
+      delta += __shfl_xor_sync(0xffffffffu, delta, 2);
+#pragma unroll
+      for (int nt = 0; nt < 2 * NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) dp[nt][2 * hrow + e] = p[nt][2 * hrow + e] * (dp[nt][2 * hrow + e] - delta);
+    }
+    g_store_rows_smem<NT>(Ds, G::SP, 16 * w, dp, g, t);
+    float o[HD / 8][4];
+    bf16* dbase = a.dqkv + row0 * ld + h * HD;
+    g_mul_regs<HD, NT>(o, dp, k_t, lane);                 // dQ rows of this warp = dS_w . K
+    g_store_global<HD>(dbase, ld, L, 16 * w, o, a.scale, g, t);
+    __syncthreads();                                      // every warp's rows of P and dS are in shared memory
+    g_mul_t<HD, NT>(o, d_t, q_t, w, lane);                // dK rows [16 w, +16) = dS^T . Q
+    g_store_global<HD>(dbase + d, ld, L, 16 * w, o, 1.f, g, t);
+    g_mul_t<HD, NT>(o, p_t, g_t, w, lane);                // dV rows = dropout(P)^T . dO
+    g_store_global<HD>(dbase + 2 * d, ld, L, 16 * w, o, 1.f, g, t);
+    __syncthreads();
+  }
+}
+
+template <int HD, int NT>
+static int launch_gmma(bool bwd, const MmaAttnArgs& a, cudaStream_t st) {
+  using G = GAttn<HD, NT>;
+  const int smem = bwd ? G::kSmemBwd : G::kSmemFwd;
+  static bool configured[2] = {false, false};
+  if (!configured[bwd ? 1 : 0]) {
+    if (bwd) DSVG_CUDA(cudaFuncSetAttribute(attn_gmma_bwd_kernel<HD, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    else DSVG_CUDA(cudaFuncSetAttribute(attn_gmma_fwd_kernel<HD, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured[bwd ? 1 : 0] = true;
+  }
+  const long long npairs = (long long)a.nseq * a.H;
+  int per_sm = (220 * 1024) / (smem + 1024);
+  if (per_sm > 2048 / G::kThreads) per_sm = 2048 / G::kThreads;
+  if (per_sm > 32) per_sm = 32;
+  if (per_sm < 1) per_sm = 1;
+  long long blocks = 148LL * per_sm;
+  if (blocks > npairs) blocks = npairs;
+  if (bwd) DSVG_CUDA(launch_k(attn_gmma_bwd_kernel<HD, NT>, dim3(int(blocks)), dim3(G::kThreads), size_t(smem), st, a));
+  else DSVG_CUDA(launch_k(attn_gmma_fwd_kernel<HD, NT>, dim3(int(blocks)), dim3(G::kThreads), size_t(smem), st, a));
+  ++g_launches;
+  return 0;
+}
+template <int HD>
+static int launch_gmma_nt(bool bwd, const MmaAttnArgs& a, cudaStream_t st) {
+  switch ((a.L + 15) / 16) {
+    case 1: return launch_gmma<HD, 1>(bwd, a, st);
+    case 2: return launch_gmma<HD, 2>(bwd, a, st);
+    case 3: return launch_gmma<HD, 3>(bwd, a, st);
+    case 4: return launch_gmma<HD, 4>(bwd, a, st);
+    case 5: return launch_gmma<HD, 5>(bwd, a, st);
+    default: DSVG_CHECK(false, "tensor-core attention: L = %d exceeds 80 positions", a.L);
+  }
+}
+
+}  // namespace dsvg
+
+// head_dim 32 / 64, L <= 80, single-plane operands
+int dsvg_attn_gmma(bool bwd, const bf16* qkv, const uint8_t* valid, bf16* out, const bf16* dout, bf16* dqkv, int nseq, int L,
+                   int H, int head_dim, float q_scale, Dropout drop, cudaStream_t st) {
+  MmaAttnArgs a{};
+  a.qkv = qkv; a.valid = valid; a.out = out; a.dout = dout; a.dqkv = dqkv; a.nseq = nseq; a.L = L; a.H = H;
+  a.scale = q_scale; a.drop = drop;
+  if (head_dim == 32) return launch_gmma_nt<32>(bwd, a, st);
+  if (head_dim == 64) return launch_gmma_nt<64>(bwd, a, st);
+  DSVG_CHECK(false, "tensor-core attention: head_dim %d unsupported", head_dim);
+}

@@ -37,8 +37,22 @@ def _digest():
 
 
 def build(force=False, verbose=False):
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    """Idempotent and safe to call from several processes at once (one rank per GPU under torchrun): an exclusive
+    file lock serialises the compilation; the ranks that waited find the stamp up to date and return."""
+    import fcntl
     dig = _digest()
+    if not force and LIB.exists() and STAMP.exists() and STAMP.read_text().strip() == dig:
+        return LIB
+    with open(PKG / ".build.lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(dig, force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(dig, force, verbose):
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     if not force and LIB.exists() and STAMP.exists() and STAMP.read_text().strip() == dig:
         return LIB
     if not Path(nvcc).exists():
@@ -66,8 +80,10 @@ def build(force=False, verbose=False):
             sys.stderr.write(f"--- {src.name} ---\n{out}\n")
     if failed:
         raise RuntimeError("nvcc compilation failed")
-    cmd = [nvcc, "-shared", "-o", str(LIB)] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    tmp = LIB.with_suffix(".so.tmp")
+    cmd = [nvcc, "-shared", "-o", str(tmp)] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
     subprocess.check_call(cmd)
+    os.replace(tmp, LIB)     # atomic: a concurrent loader never maps a half-written library
     STAMP.write_text(dig)
     return LIB
 

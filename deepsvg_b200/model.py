@@ -265,8 +265,15 @@ class SVGTransformer(nn.Module):
         ref = commands_enc if commands_enc is not None else z
         if not ref.is_cuda:
             raise RuntimeError("deepsvg_b200 has no CPU path: inputs and parameters must live on a CUDA device")
-        if cfg.label_condition and label is None:
-            raise ValueError("label_condition=True needs `label`")
+        if cfg.label_condition:
+            if label is None:
+                raise ValueError("label_condition=True needs `label`")
+            # the kernels read `const long long*` through a raw pointer: normalise dtype / device / layout here
+            label = label.to(device=ref.device, dtype=torch.long).contiguous().view(-1)
+            if label.numel() != ref.shape[0]:
+                raise ValueError("label must hold one class id per icon (%d), got %d" % (ref.shape[0], label.numel()))
+            if os.environ.get("DSVG_DEBUG_CHECKS") and (int(label.min()) < 0 or int(label.max()) >= cfg.n_labels):
+                raise ValueError("label ids must lie in [0, n_labels)")
         inputs = dict(commands=commands_enc, args=args_enc, label=label, z=z, encode_mode=encode_mode,
                       return_hierarch=return_hierarch, training=self.training)
         plist = [self._param(n) for n in self._pnames]
@@ -359,6 +366,8 @@ class SVGTransformer(nn.Module):
     def _pack(self, name, need_t=True):
         p = self._param(name)
         key = (p.data_ptr(), p._version, self.planes, p.device)
+        # keyed per device: nn.DataParallel replicas share this dict (shallow-copied __dict__) and run in threads
+        name = (name, p.device)
         hit = self._wcache.get(name)
         if hit is not None and hit[0] == key:
             return hit[1], hit[2]

@@ -12,6 +12,8 @@ from . import _lib
 
 
 class FusedAdamW(torch.optim.Optimizer):
+    RING = 4
+
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_grad_norm=None):
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, max_grad_norm=max_grad_norm)
         super().__init__(params, defaults)
@@ -20,6 +22,11 @@ class FusedAdamW(torch.optim.Optimizer):
     def _group_state(self, gi, group):
         st = self._flat.get(gi)
         ps = [p for p in group["params"] if p.requires_grad]
+        if st is not None and st["ids"] != [id(p) for p in ps]:
+            # the set of trainable parameters changed (requires_grad toggled, add_param_group): the flat moment buffers
+            # are laid out per parameter, so carry the existing moments over by identity and rebuild the table
+            st = self._rebuild(st, ps)
+            self._flat[gi] = st
         if st is None or st["device"] != ps[0].device:
             n = sum(p.numel() for p in ps)
             dev = ps[0].device
@@ -30,11 +37,39 @@ class FusedAdamW(torch.optim.Optimizer):
                 rows.append((off, p.numel()))
                 off += p.numel()
             st["rows"] = rows
-            st["host"] = torch.zeros(len(ps), 5, dtype=torch.int64).pin_memory()
-            st["dev"] = torch.zeros(len(ps), 5, dtype=torch.int64, device=dev)
+            st["ids"] = [id(p) for p in ps]
+            # Ring of pinned pointer tables: the H2D copy of slot i is asynchronous, so the host may only rewrite slot
+            # i after the copy enqueued from it has executed (event per slot).  The GPU-bound train loop lets the host
+            # run several steps ahead; a single table would be overwritten under a queued copy.
+            st["host"] = [torch.zeros(len(ps), 5, dtype=torch.int64).pin_memory() for _ in range(self.RING)]
+            st["dev"] = [torch.zeros(len(ps), 5, dtype=torch.int64, device=dev) for _ in range(self.RING)]
+            st["done"] = [None] * self.RING
+            st["slot"] = 0
             st["chunks"] = min(64, max(1, math.ceil(max(p.numel() for p in ps) / 4096)))
             self._flat[gi] = st
         return st, ps
+
+    def _rebuild(self, old, ps):
+        dev = ps[0].device
+        n = sum(p.numel() for p in ps)
+        st = dict(device=dev, step=old["step"], m=torch.zeros(n, device=dev), v=torch.zeros(n, device=dev),
+                  sq=torch.zeros(1, device=dev))
+        where = {i: r for i, r in zip(old["ids"], old["rows"])}
+        off, rows = 0, []
+        for p in ps:
+            rows.append((off, p.numel()))
+            prev = where.get(id(p))
+            if prev is not None and old["device"] == dev:
+                st["m"][off:off + p.numel()].copy_(old["m"][prev[0]:prev[0] + prev[1]])
+                st["v"][off:off + p.numel()].copy_(old["v"][prev[0]:prev[0] + prev[1]])
+            off += p.numel()
+        st["rows"], st["ids"] = rows, [id(p) for p in ps]
+        st["host"] = [torch.zeros(len(ps), 5, dtype=torch.int64).pin_memory() for _ in range(self.RING)]
+        st["dev"] = [torch.zeros(len(ps), 5, dtype=torch.int64, device=dev) for _ in range(self.RING)]
+        st["done"] = [None] * self.RING
+        st["slot"] = 0
+        st["chunks"] = min(64, max(1, math.ceil(max(p.numel() for p in ps) / 4096)))
+        return st
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -48,7 +83,11 @@ class FusedAdamW(torch.optim.Optimizer):
             st, ps = self._group_state(gi, group)
             if not ps[0].is_cuda:
                 raise RuntimeError("deepsvg_b200.FusedAdamW has no CPU path")
-            host = st["host"]
+            slot = st["slot"]
+            st["slot"] = (slot + 1) % self.RING
+            if st["done"][slot] is not None:
+                st["done"][slot].synchronize()      # the copy that last read this pinned slot has executed
+            host, table = st["host"][slot], st["dev"][slot]
             keep = []
             for i, (p, (off, n)) in enumerate(zip(ps, st["rows"])):
                 g = p.grad
@@ -61,7 +100,10 @@ class FusedAdamW(torch.optim.Optimizer):
                 host[i, 0], host[i, 1] = p.data_ptr(), g.data_ptr()
                 host[i, 2], host[i, 3] = st["m"].data_ptr() + 4 * off, st["v"].data_ptr() + 4 * off
                 host[i, 4] = n
-            st["dev"].copy_(host, non_blocking=True)
+            table.copy_(host, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            st["done"][slot] = ev
             st["step"] += 1
             b1, b2 = group["betas"]
             t = st["step"]
@@ -69,11 +111,14 @@ class FusedAdamW(torch.optim.Optimizer):
             sq = 0
             if mx is not None and mx > 0:
                 st["sq"].zero_()
-                _lib.check(lib.dsvg_grad_sqnorm(st["dev"].data_ptr(), len(ps), st["chunks"], st["sq"].data_ptr(), stream),
+                _lib.check(lib.dsvg_grad_sqnorm(table.data_ptr(), len(ps), st["chunks"], st["sq"].data_ptr(), stream),
                            "dsvg_grad_sqnorm")
                 sq = st["sq"].data_ptr()
-            _lib.check(lib.dsvg_adamw_step(st["dev"].data_ptr(), len(ps), st["chunks"], group["lr"], b1, b2, group["eps"],
+            _lib.check(lib.dsvg_adamw_step(table.data_ptr(), len(ps), st["chunks"], group["lr"], b1, b2, group["eps"],
                                            group["weight_decay"], 1.0 - b1 ** t, 1.0 - b2 ** t,
                                            float(mx) if mx else 0.0, sq, stream), "dsvg_adamw_step")
             self._keep = keep   # contiguous gradient copies must outlive the asynchronous launch
+            # The kernels wrote the parameters through raw pointers: tell autograd / version-keyed caches (the model's
+            # bf16 weight-operand cache is keyed on `_version`) that every parameter changed.
+            torch._C._increment_version([p for p in ps if p.grad is not None])
         return loss

@@ -68,6 +68,12 @@ CASES = {
     # the same edge batch at a configuration the CUDA path supports (head_dim 32), for the GPU parity test
     "edge_d128": ("hierarchical", dict(use_vae=False, d_model=128, n_heads=4, dim_feedforward=256, dim_z=64, n_layers=2,
                                        n_layers_decode=2, max_num_groups=4, max_seq_len=10), 4, False),
+    # BASELINE.json configs[4] ("scaled hierarchical, tensor-core stress"): d_model 512, 8 layers per
+    # stack, 16 paths of 64 commands, head_dim 64; 55.8 M parameters are regenerated from the seed, only outputs are stored
+    "scaled_cfg5": ("hierarchical", dict(use_vae=False, d_model=512, n_layers=8, n_layers_decode=8, max_num_groups=16,
+                                         max_seq_len=64), 2, False),
+    # BASELINE.json configs[3] (one-stage fonts): G = 1 grouped tensors of 50 commands, 52 labels, VAE
+    "fonts_cfg4": ("one_stage", dict(use_vae=True, label_condition=True, n_labels=52, max_total_len=50), 3, False),
 }
 
 

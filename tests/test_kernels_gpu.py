@@ -269,6 +269,62 @@ def test_attention_mma_fast_path(L, masked, nseq):
         assert e.item() < 1.5e-2, (nm, e.item())
 
 
+@pytest.mark.parametrize("L,H,hd,masked,nseq", [(52, 8, 32, True, 40), (51, 8, 32, False, 40), (66, 8, 64, True, 33),
+                                                (65, 8, 64, False, 33), (16, 8, 64, True, 50), (33, 4, 32, True, 3000),
+                                                (80, 2, 64, True, 7), (8, 8, 64, True, 64)])
+def test_attention_general_tensor_core_path(L, H, hd, masked, nseq):
+    """Single-plane bf16, head_dim 32 / 64, L <= 80 (one-stage fonts L = 52 / 51, scaled hierarchical L = 66 / 65 and
+    16 group-level) -> attn_gmma kernels (CTA per (sequence, head), warp per 16-row query tile).  Same bound as the
+    32 x 32 fast path: P and dS are rounded to bf16 inside."""
+    ops = _ops()
+    d, M = H * hd, nseq * L
+    qa = ops.act_from_float(_rand(M, 3 * d, seed=1, scale=0.7), 1)
+    qv = qa.float().clone().requires_grad_(True)
+    valid = vmask = None
+    if masked:
+        lens = torch.randint(1, L + 1, (nseq,), generator=torch.Generator().manual_seed(3))
+        vmask = (torch.arange(L)[None, :] < lens[:, None]).to(DEV)
+        valid = vmask.to(torch.uint8).reshape(-1).contiguous()
+    out = ops.Act(M, d, 1, DEV)
+    ops.attn_fwd(qa, valid, out, nseq, L, H, hd, (0.0, 0, 0))
+    q, k, v = (t.reshape(nseq, L, H, hd).transpose(1, 2) for t in qv.split(d, dim=-1))
+    s = q @ k.transpose(-1, -2)
+    if masked:
+        s = s.masked_fill(~vmask[:, None, None, :], float("-inf"))
+    ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(M, d)
+    assert _rel(out.float(), ref.detach()) < 1.5e-2
+    da = ops.act_from_float(_rand(M, d, seed=5), 1)
+    ref.backward(da.float())
+    dqkv = ops.Act(M, 3 * d, 1, DEV)
+    ops.attn_bwd(qa, valid, da, dqkv, nseq, L, H, hd, 0.5, (0.0, 0, 0))
+    g = qv.grad.clone()
+    g[:, :d] *= 0.5
+    for lo, hi, nm in ((0, d, "dq"), (d, 2 * d, "dk"), (2 * d, 3 * d, "dv")):
+        e = (dqkv.float()[:, lo:hi] - g[:, lo:hi]).norm() / g[:, lo:hi].norm()
+        assert e.item() < 1.5e-2, (nm, e.item())
+
+
+def test_attention_general_path_dropout_consistent():
+    ops = _ops()
+    nseq, L, H, hd = 9, 66, 8, 64
+    d, M = H * hd, nseq * L
+    qa = ops.act_from_float(_rand(M, 3 * d, seed=1, scale=0.5), 1)
+    drop = (0.3, 11, 99)
+    o1, o2, o0 = ops.Act(M, d, 1, DEV), ops.Act(M, d, 1, DEV), ops.Act(M, d, 1, DEV)
+    ops.attn_fwd(qa, None, o1, nseq, L, H, hd, drop)
+    ops.attn_fwd(qa, None, o2, nseq, L, H, hd, drop)
+    ops.attn_fwd(qa, None, o0, nseq, L, H, hd, (0.0, 0, 0))
+    assert torch.equal(o1.t, o2.t) and not torch.equal(o1.t, o0.t)
+    ga = ops.act_from_float(_rand(M, d, seed=2), 1)
+    dqkv = ops.Act(M, 3 * d, 1, DEV)
+    ops.attn_bwd(qa, None, ga, dqkv, nseq, L, H, hd, 1.0, drop)
+    lhs = (o1.float() * ga.float()).sum().item()
+    rhs = (qa.float()[:, 2 * d:] * dqkv.float()[:, 2 * d:]).sum().item()
+    assert abs(lhs - rhs) < 2e-2 * abs(lhs)
+    # dropout keeps the mean: E[out] = out(no dropout)
+    assert abs(o1.float().mean().item() - o0.float().mean().item()) < 5e-3 * o0.float().abs().mean().item() + 1e-4
+
+
 @pytest.mark.parametrize("planes", [1, 2])
 def test_attention_dropout_consistent_fwd_bwd(planes):
     """With dropout the backward must use the forward's mask: check d(out . w)/dv against finite structure."""
