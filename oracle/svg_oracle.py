@@ -212,7 +212,13 @@ def _layer_norm(x, w, b):
     return F.layer_norm(x, (x.shape[-1],), w, b, 1e-5)  # improved_transformer.py:35-36 (nn.LayerNorm default eps)
 
 
-def _self_attention(mm, x, p, pre, n_heads, key_pad):
+def _drop(x, p):
+    """train-mode dropout (torch's own RNG).  p = 0 (parity runs, eval mode) is the identity; p > 0 is used only by
+    bench.py's CPU / stock-GPU baseline legs so that the timed arithmetic matches the reference's `model.train()` step."""
+    return F.dropout(x, p, training=True) if p > 0 else x
+
+
+def _self_attention(mm, x, p, pre, n_heads, key_pad, drop=0.0):
     """functional.py:92-249 for query is key is value.  x [..., L, d]; key_pad bool [..., L] True = ignore key."""
     d = x.shape[-1]
     hd = d // n_heads
@@ -224,30 +230,30 @@ def _self_attention(mm, x, p, pre, n_heads, key_pad):
     s = mm.mm(q, k.transpose(-1, -2))                                                     # :228
     if key_pad is not None:
         s = s.masked_fill(key_pad[..., None, None, :], float("-inf"))                     # :235-240
-    a = torch.softmax(s, dim=-1)                                                          # :243
+    a = _drop(torch.softmax(s, dim=-1), drop)                                             # :243-244
     o = mm.mm(a, v).transpose(-2, -3).reshape(x.shape)                                    # :246-248
     return mm.linear(o, p[pre + ".out_proj.weight"], p[pre + ".out_proj.bias"])          # :249
 
 
-def _layer(mm, x, p, pre, n_heads, key_pad, zglob, lab):
+def _layer(mm, x, p, pre, n_heads, key_pad, zglob, lab, drop=0.0):
     """Pre-LN block: improved_transformer.py:42-54 (encoder) / :126-141 (decoder with linear_global).
     zglob / lab broadcast over the sequence axis (-2)."""
-    h = x + _self_attention(mm, _layer_norm(x, p[pre + ".norm1.weight"], p[pre + ".norm1.bias"]), p,
-                            pre + ".self_attn", n_heads, key_pad)
+    h = x + _drop(_self_attention(mm, _layer_norm(x, p[pre + ".norm1.weight"], p[pre + ".norm1.bias"]), p,
+                                  pre + ".self_attn", n_heads, key_pad, drop), drop)
     if zglob is not None:
-        h = h + mm.linear(zglob, p[pre + ".linear_global.weight"], p[pre + ".linear_global.bias"]).unsqueeze(-2)
+        h = h + _drop(mm.linear(zglob, p[pre + ".linear_global.weight"], p[pre + ".linear_global.bias"]), drop).unsqueeze(-2)
     if lab is not None:
-        h = h + mm.linear(lab, p[pre + ".linear_global2.weight"], p[pre + ".linear_global2.bias"]).unsqueeze(-2)
+        h = h + _drop(mm.linear(lab, p[pre + ".linear_global2.weight"], p[pre + ".linear_global2.bias"]), drop).unsqueeze(-2)
     f = _layer_norm(h, p[pre + ".norm2.weight"], p[pre + ".norm2.bias"])
-    f = mm.linear(torch.relu(mm.linear(f, p[pre + ".linear1.weight"], p[pre + ".linear1.bias"])),
+    f = mm.linear(_drop(torch.relu(mm.linear(f, p[pre + ".linear1.weight"], p[pre + ".linear1.bias"])), drop),
                   p[pre + ".linear2.weight"], p[pre + ".linear2.bias"])
-    return h + f
+    return h + _drop(f, drop)
 
 
-def _stack(mm, x, p, pre, n_layers, n_heads, key_pad=None, zglob=None, lab=None):
+def _stack(mm, x, p, pre, n_layers, n_heads, key_pad=None, zglob=None, lab=None, drop=0.0):
     """transformer.py:168-188 / :214-242: L layers then the final LayerNorm."""
     for i in range(n_layers):
-        x = _layer(mm, x, p, f"{pre}.layers.{i}", n_heads, key_pad, zglob, lab)
+        x = _layer(mm, x, p, f"{pre}.layers.{i}", n_heads, key_pad, zglob, lab, drop)
     return _layer_norm(x, p[pre + ".norm.weight"], p[pre + ".norm.bias"])
 
 
@@ -277,10 +283,14 @@ def group_index(cmd):      # number of "m" so far                  (model/utils.
 # --------------------------------------------------------------------------------------------------
 # forward (model.py:352-412), eval mode (no dropout); VAE noise is an input
 # --------------------------------------------------------------------------------------------------
-def forward(params, cfg, commands, args, label=None, eps=None, matmul="fp32", z_in=None):
+def forward(params, cfg, commands, args, label=None, eps=None, matmul="fp32", z_in=None, train_dropout=False):
     """commands [N,G,L] / args [N,G,L,11] float (encoder == decoder inputs, as model/config.py:47-60 wires them).
-    Returns the reference's result dict (batch-first) plus 'z' [N, dz]."""
+    Returns the reference's result dict (batch-first) plus 'z' [N, dz].
+    train_dropout: draw the reference's train-mode dropout masks (cfg.dropout; 0.1 at the positional encodings,
+    positional_encoding.py:26) -- baseline timing only, parity always runs eval-mode arithmetic."""
     mm = _MM(matmul)
+    dr = float(cfg.dropout) if train_dropout else 0.0
+    dr_pe = 0.1 if train_dropout else 0.0
     p = params
     dt = p["decoder.fcn.args_fcn.weight"].dtype
     N, G, L = commands.shape
@@ -297,18 +307,18 @@ def forward(params, cfg, commands, args, label=None, eps=None, matmul="fp32", z_
             mm.linear(emb, p["encoder.embedding.embed_fcn.weight"], p["encoder.embedding.embed_fcn.bias"])
         if not two_e:
             x = x + p["encoder.embedding.group_embed.weight"][group_index(cmd)]
-        x = x + p["encoder.embedding.pos_encoding.pos_embed.weight"][:L]              # positional_encoding.py:40-43
+        x = _drop(x + p["encoder.embedding.pos_encoding.pos_embed.weight"][:L], dr_pe)  # positional_encoding.py:40-43
         kp = key_padding(cmd)
         lab_e = p["encoder.label_embedding.label_embedding.weight"][label] if cfg.label_condition else None
         # ---- E1 (model.py:135) + masked mean over positions (:137) ----
         mem = _stack(mm, x, p, "encoder.encoder", cfg.n_layers, H, kp,
-                     lab=None if lab_e is None else lab_e[:, None, :].expand(N, G, -1))
+                     lab=None if lab_e is None else lab_e[:, None, :].expand(N, G, -1), drop=dr)
         w = (~kp).to(dt).unsqueeze(-1)
         z = (mem * w).sum(-2) / w.sum(-2)                                                 # [N,G,d]
         if two_e:
             vis = visibility(cmd)                                                         # [N,G]
-            z = z + p["encoder.hierarchical_PE.pos_embed.weight"][:G]                      # model.py:158
-            mem2 = _stack(mm, z, p, "encoder.hierarchical_encoder", cfg.n_layers, H, ~vis, lab=lab_e)   # :160
+            z = _drop(z + p["encoder.hierarchical_PE.pos_embed.weight"][:G], dr_pe)        # model.py:158
+            mem2 = _stack(mm, z, p, "encoder.hierarchical_encoder", cfg.n_layers, H, ~vis, lab=lab_e, drop=dr)   # :160
             wv = vis.to(dt).unsqueeze(-1)
             z = (mem2 * wv).sum(-2) / wv.sum(-2)                                           # :161  [N,d]
         else:
@@ -335,8 +345,8 @@ def forward(params, cfg, commands, args, label=None, eps=None, matmul="fp32", z_
     lab_d = p["decoder.label_embedding.label_embedding.weight"][label] if cfg.label_condition else None
     if two_d:
         Gp = cfg.num_groups_proposal
-        src = p["decoder.hierarchical_embedding.PE.pos_embed.weight"][:Gp].unsqueeze(0).expand(N, Gp, -1)   # :251
-        out = _stack(mm, src, p, "decoder.hierarchical_decoder", cfg.n_layers_decode, H, None, zglob=z, lab=lab_d)
+        src = _drop(p["decoder.hierarchical_embedding.PE.pos_embed.weight"][:Gp].unsqueeze(0).expand(N, Gp, -1), dr_pe)   # :251
+        out = _stack(mm, src, p, "decoder.hierarchical_decoder", cfg.n_layers_decode, H, None, zglob=z, lab=lab_d, drop=dr)
         vis_logits = mm.linear(out, p["decoder.hierarchical_fcn.visibility_fcn.weight"],
                                p["decoder.hierarchical_fcn.visibility_fcn.bias"])          # basic_blocks.py:36
         zp = mm.linear(out, p["decoder.hierarchical_fcn.z_fcn.weight"], p["decoder.hierarchical_fcn.z_fcn.bias"])
@@ -347,8 +357,8 @@ def forward(params, cfg, commands, args, label=None, eps=None, matmul="fp32", z_
         zmem, Gd = z[:, None, :], 1
         lab_d1 = None if lab_d is None else lab_d[:, None, :]
     Ld = (cfg.max_seq_len if two_d else cfg.max_total_len) + 1
-    src = p["decoder.embedding.PE.pos_embed.weight"][:Ld].reshape(1, 1, Ld, -1).expand(N, Gd, Ld, -1)       # :278
-    out = _stack(mm, src, p, "decoder.decoder", cfg.n_layers_decode, H, None, zglob=zmem, lab=lab_d1)        # :279
+    src = _drop(p["decoder.embedding.PE.pos_embed.weight"][:Ld].reshape(1, 1, Ld, -1).expand(N, Gd, Ld, -1), dr_pe)   # :278
+    out = _stack(mm, src, p, "decoder.decoder", cfg.n_layers_decode, H, None, zglob=zmem, lab=lab_d1, drop=dr)        # :279
     res["command_logits"] = mm.linear(out, p["decoder.fcn.command_fcn.weight"], p["decoder.fcn.command_fcn.bias"])
     al = mm.linear(out, p["decoder.fcn.args_fcn.weight"], p["decoder.fcn.args_fcn.bias"])
     res["args_logits"] = al.reshape(N, Gd, Ld, cfg.n_args, cfg.args_dim + 1)                # basic_blocks.py:21
@@ -380,7 +390,7 @@ def loss(out, cfg, weights=DEFAULT_WEIGHTS):
         total = total + weights["loss_visibility_weight"] * lv
         res["loss_visibility"] = lv
     tc1, ta1 = tc[..., 1:], ta[..., 1:, :]
-    wa = CMD_ARGS_MASK[tc1].to(wc.dtype)                                                   # :51
+    wa = CMD_ARGS_MASK.to(tc1.device)[tc1].to(wc.dtype)                                    # :51
     cl, al = out["command_logits"], out["args_logits"]
     ce_c = F.cross_entropy(cl.reshape(-1, cl.shape[-1]), tc1.reshape(-1), reduction="none").reshape(tc1.shape)
     ce_a = F.cross_entropy(al.reshape(-1, al.shape[-1]), (ta1.long() + 1).reshape(-1),
@@ -392,10 +402,11 @@ def loss(out, cfg, weights=DEFAULT_WEIGHTS):
     return res
 
 
-def train_step(params, cfg, commands, args, label=None, eps=None, weights=DEFAULT_WEIGHTS, matmul="fp32"):
-    """forward + loss + backward (train.py:94-98, eval-mode arithmetic).  Returns (out, losses, grads)."""
+def train_step(params, cfg, commands, args, label=None, eps=None, weights=DEFAULT_WEIGHTS, matmul="fp32",
+               train_dropout=False):
+    """forward + loss + backward (train.py:94-98; eval-mode arithmetic unless train_dropout).  Returns (out, losses, grads)."""
     leaves = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
-    out = forward(leaves, cfg, commands, args, label=label, eps=eps, matmul=matmul)
+    out = forward(leaves, cfg, commands, args, label=label, eps=eps, matmul=matmul, train_dropout=train_dropout)
     ls = loss(out, cfg, weights)
     ls["loss"].backward()
     grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaves.items()}
