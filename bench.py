@@ -386,9 +386,9 @@ def run_ours(a):
     extra = settle(step, step_e2e)
     if sampler:
         sampler.recording = True
-    l0 = _lib.launch_count()
+    l0 = _lib.launch_count() + model.graph_kernel_launches
     ms = timed(lambda: step(cmd_d, arg_d, lab_d), a.steps)
-    launches = (_lib.launch_count() - l0) / a.steps
+    launches = (_lib.launch_count() + model.graph_kernel_launches - l0) / a.steps
     for _ in range(5):
         step_e2e()
     ms_e2e = timed(step_e2e, a.steps)
@@ -426,6 +426,11 @@ def run_ours(a):
 
     # ---- the tolerance-meeting mode (bf16x3: rtol 1e-3 / atol 1e-4 vs the fp32 reference, tests/test_model_gpu.py) timed too --
     parity = None
+    graphed = getattr(model, "_gs", None) is not None
+    graph_backward = graphed and model._gs.bwd_a is not None
+    if hasattr(model, "release_graphs"):
+        model.release_graphs()          # frees the captured step's private pool (one step of activations)
+        torch.cuda.empty_cache()
     if a.precision == "bf16" and not a.no_parity_mode:
         pm = SVGTransformer(cfg, precision="bf16x3", process_group=pg).to(dev)
         pm.load_state_dict(model.state_dict())
@@ -441,9 +446,12 @@ def run_ours(a):
         parity = {"precision": "bf16x3 (split-bf16 operands, 3 tcgen05 products per K step)", "steps": k,
                   "value": world * B * k / (pms / 1e3), "ms_per_step": pms / k,
                   "e2e": world * B * k / (pms_e2e / 1e3), "unit": "icons/s", "final_loss": float(loss_host.item()),
+                  "cuda_graphs": getattr(pm, "_gs", None) is not None,
                   "tolerance": "logits/loss rtol 1e-3 atol 1e-4 vs the fp32 reference; argmax identical wherever the "
                                "reference's own top-2 margin exceeds 2e-4 (tests/test_model_gpu.py)"}
+        pm.release_graphs()
         del pm, pstep, pe2e
+        torch.cuda.empty_cache()
 
     # ---- data-parallel self-check (N > 1): all-reduced per-rank gradients == single-process gradient of the global batch --
     ddp = None
@@ -500,6 +508,8 @@ def run_ours(a):
         "dtype": "bf16" if a.precision == "bf16" else "bf16x3(split-bf16, fp32-accurate)", "data": "synthetic",
         "config": cfgd,
         "run": {"final_loss": final_loss, "extra_untimed_warmup_steps": extra,
+                "cuda_graphs": {"forward": graphed, "backward": graph_backward,
+                                "note": "gpu_launches counts the kernels inside the replayed graphs plus the eager loss kernels"},
                 "argmax_note": "bit-exact argmax is asserted (parity mode) where the reference's top-2 margin > 2e-4"},
         "e2e": {"value": ips_e2e, "unit": "icons/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / a.steps},

@@ -83,6 +83,7 @@ __device__ __forceinline__ void stage_rows(float* dst, const bf16* p, size_t lo,
 
 template <int HD>
 __global__ void __launch_bounds__(128) attn_fwd_kernel(AttnArgs a) {
+  drop_resolve(a.drop);
   extern __shared__ __align__(16) float smem[];
   const int wpb = blockDim.x >> 5, wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = a.L, Lp = L | 1, d = a.H * HD, ld = 3 * d;
@@ -134,6 +135,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(AttnArgs a) {
 
 template <int HD>
 __global__ void __launch_bounds__(128) attn_bwd_kernel(AttnArgs a) {
+  drop_resolve(a.drop);
   extern __shared__ __align__(16) float smem[];
   const int wpb = blockDim.x >> 5, wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = a.L, Lp = L | 1, d = a.H * HD, ld = 3 * d;

@@ -267,6 +267,7 @@ constexpr int kMmaWarps = 4;
 __global__ void __launch_bounds__(kMmaWarps * 32) attn_mma_fwd_kernel(MmaAttnArgs a) {
   pdl_launch_dependents();
   pdl_wait();
+  drop_resolve(a.drop);
   __shared__ __align__(16) bf16 sm[kMmaWarps][3 * kTile];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int L = a.L, d = a.H * 32, ld = 3 * d;
@@ -307,6 +308,7 @@ __global__ void __launch_bounds__(kMmaWarps * 32) attn_mma_fwd_kernel(MmaAttnArg
 __global__ void __launch_bounds__(kMmaWarps * 32) attn_mma_bwd_kernel(MmaAttnArgs a) {
   pdl_launch_dependents();
   pdl_wait();
+  drop_resolve(a.drop);
   extern __shared__ __align__(16) bf16 sm_dyn[];   // kMmaWarps x 6 tiles (60 KB: above the static limit)
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int L = a.L, d = a.H * 32, ld = 3 * d;
@@ -630,6 +632,7 @@ __global__ void __launch_bounds__(32 * NT) attn_gmma_fwd_kernel(MmaAttnArgs a) {
   using G = GAttn<HD, NT>;
   pdl_launch_dependents();
   pdl_wait();
+  drop_resolve(a.drop);
   extern __shared__ __align__(16) bf16 sm_dyn[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int L = a.L, d = a.H * HD, ld = 3 * d;
@@ -671,6 +674,7 @@ __global__ void __launch_bounds__(32 * NT) attn_gmma_bwd_kernel(MmaAttnArgs a) {
   using G = GAttn<HD, NT>;
   pdl_launch_dependents();
   pdl_wait();
+  drop_resolve(a.drop);
   extern __shared__ __align__(16) bf16 sm_dyn[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int L = a.L, d = a.H * HD, ld = 3 * d;

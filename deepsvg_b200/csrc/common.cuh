@@ -101,20 +101,39 @@ struct Dropout {
   float p;             // requested drop probability; 0 disables
   uint32_t thr16;      // keep iff 16-bit draw >= thr16
   float scale;         // 1 / (1 - thr16 / 65536)
-  uint32_t key;        // mixes seed and call-site id (host-computed)
+  uint32_t key;        // mixes seed and call-site id (host-computed, or resolved in the kernel from *seed_dev)
+  const unsigned long long* seed_dev;  // non-null: the seed lives in device memory (CUDA-graph replays draw new masks)
+  uint32_t site;
 };
-inline uint32_t host_mix32(uint32_t x) {
+__host__ __device__ inline uint32_t host_mix32(uint32_t x) {
   x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
   return x;
 }
+__host__ __device__ inline uint32_t drop_key_of(unsigned long long seed, uint32_t site) {
+  return host_mix32(uint32_t(seed) ^ host_mix32(uint32_t(seed >> 32) + 0x9E3779B9u * (site + 1u)));
+}
+// C ABI convention (include/dsvg_b200.h): bit 31 of `drop_site` set => `seed` is a DEVICE POINTER to the uint64 seed,
+// read by the kernel at run time (so a captured CUDA graph draws fresh masks on every replay).
+constexpr uint32_t kSeedIsDevicePtr = 0x80000000u;
 inline Dropout make_dropout(float p, uint32_t site, unsigned long long seed) {
   Dropout d;
   d.p = p;
   double t = double(p) * 65536.0 + 0.5;
   d.thr16 = t >= 65535.0 ? 65535u : (t <= 0.0 ? 0u : uint32_t(t));
   d.scale = 1.f / (1.f - float(d.thr16) / 65536.f);
-  d.key = host_mix32(uint32_t(seed) ^ host_mix32(uint32_t(seed >> 32) + 0x9E3779B9u * (site + 1u)));
+  d.site = site & ~kSeedIsDevicePtr;
+  if (site & kSeedIsDevicePtr) {
+    d.seed_dev = reinterpret_cast<const unsigned long long*>(static_cast<uintptr_t>(seed));
+    d.key = 0;
+  } else {
+    d.seed_dev = nullptr;
+    d.key = drop_key_of(seed, d.site);
+  }
   return d;
+}
+// every kernel that draws dropout masks calls this once (after pdl_wait: the seed may be written by a preceding kernel)
+__device__ __forceinline__ void drop_resolve(Dropout& d) {
+  if (d.p > 0.f && d.seed_dev != nullptr) d.key = drop_key_of(__ldg(d.seed_dev), d.site);
 }
 // key' for a quad index (the high word is zero for every tensor below 2^34 elements, but stays part of the definition)
 __device__ __forceinline__ uint32_t drop_hikey(const Dropout& d, unsigned long long quad) {

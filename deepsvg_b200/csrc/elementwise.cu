@@ -15,6 +15,7 @@ cast_act_kernel(const float* __restrict__ in, int ld_in, int R, int C, bf16* __r
                 int ld_mask, float mask_scale, Dropout drop) {
   pdl_launch_dependents();
   pdl_wait();
+  drop_resolve(drop);
   __shared__ float tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 rows per pass
@@ -57,6 +58,7 @@ seg_sum_kernel(const float* __restrict__ in, int nseq, int L, int d, bf16* __res
                float* __restrict__ out_f32, Dropout drop) {
   pdl_launch_dependents();
   pdl_wait();
+  drop_resolve(drop);
   const size_t n = size_t(nseq) * d;
   for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
     const size_t q = i / d, c = i % d;

@@ -128,6 +128,7 @@ struct EmbedArgs {
 
 template <int NV>
 __global__ void __launch_bounds__(256) embed_fwd_kernel(EmbedArgs a) {
+  drop_resolve(a.drop);
   constexpr int d = NV * 128;
   const int lane = threadIdx.x & 31;
   const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -193,6 +194,7 @@ struct EmbedBwdArgs {
 // time so that eight independent row loads per thread are in flight.  (The first version walked the tokens one by one
 // with the id loads, the dx load and the reductions in one dependent chain: 380 us per launch at N = 512, latency-bound.)
 __global__ void __launch_bounds__(512) embed_bwd_kernel(EmbedBwdArgs a) {
+  drop_resolve(a.drop);
   extern __shared__ float sm[];  // [7 + n_grp][d] accumulators | int cmd[ntok] | int grp[ntok] | int used[ntok] | int arg[ntok][n_args]
   const int c = threadIdx.x;
   const int d = a.d, L = a.L, na = a.n_args;
@@ -313,6 +315,7 @@ unfold_dW_kernel(const float* __restrict__ dT, const float* __restrict__ Ea, flo
 __global__ void __launch_bounds__(256)
 rows_embed_fwd_kernel(const float* __restrict__ add, const float* __restrict__ tab, float* __restrict__ x, int R,
                       int L, int d, Dropout drop) {
+  drop_resolve(drop);
   const size_t n4 = size_t(R) * d / 4;
   for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += size_t(gridDim.x) * blockDim.x) {
     const size_t idx = i * 4;
@@ -330,6 +333,7 @@ rows_embed_fwd_kernel(const float* __restrict__ add, const float* __restrict__ t
 __global__ void __launch_bounds__(512)
 rows_embed_bwd_kernel(const float* __restrict__ dx, float* __restrict__ dadd, float* __restrict__ dtab, int nseq, int L,
                       int d, int spb, Dropout drop) {
+  drop_resolve(drop);
   const int c = threadIdx.x;
   const int q0 = blockIdx.x * spb, q1 = min(nseq, q0 + spb);
   for (int s = 0; s < L; ++s) {

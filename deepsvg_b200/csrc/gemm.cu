@@ -768,6 +768,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     }
   } else {
     // =================== epilogue warps (2 .. 2 + kEpiWarps) ===================
+    drop_resolve(ep.drop);
     const int quarter = warp & 3;         // TMEM lane quarter this warp may read
     const int half = (warp - 2) >> 2;     // which 32-column chunk of every kCols-wide pass this warp drains
     const uint32_t stage_buf = smem_u32(staging) + (warp - 2) * kStageWarpBytes;

@@ -171,6 +171,7 @@ template <int NV>
 __global__ void __launch_bounds__(kLnWarps * 32) ln_bwd_kernel(LnBwdArgs a) {
   pdl_launch_dependents();
   pdl_wait();
+  drop_resolve(a.drop);
   constexpr int D = NV * 128;
   constexpr float invD = 1.f / float(D);
   __shared__ float red[kLnWarps][D];

@@ -36,9 +36,14 @@ class _FusedLoss(torch.autograd.Function):
             e = gl * float(weight)
             return e + g if g is not None else e
 
-        h.scales = torch.stack([eff(w.get("loss_args_weight", 0.0), g_args), eff(w.get("loss_cmd_weight", 0.0), g_cmd),
-                                eff(w.get("loss_visibility_weight", 0.0), g_vis),
-                                eff(w.get("loss_kl_weight", 0.0), g_kl)]).float().contiguous()
+        sc = torch.stack([eff(w.get("loss_args_weight", 0.0), g_args), eff(w.get("loss_cmd_weight", 0.0), g_cmd),
+                          eff(w.get("loss_visibility_weight", 0.0), g_vis),
+                          eff(w.get("loss_kl_weight", 0.0), g_kl)]).float().contiguous()
+        bufs = getattr(h, "bufs", None)
+        if bufs is not None:
+            bufs["scales"].copy_(sc)       # the captured backward graphs read the static buffer
+            sc = bufs["scales"]
+        h.scales = sc
         n_logits = len(ctx.needs_input_grad) - 5
         return (None, None, None, None, torch.ones((), device=dev)) + (None,) * n_logits
 
@@ -112,26 +117,35 @@ class SVGLoss(nn.Module):
         planes = getattr(h, "planes", 1)
         pg = getattr(h, "process_group", None) or self.process_group
         world = 1
-        first_eos = torch.empty(nseq, dtype=torch.int32, device=dev)
-        visible = torch.empty(nseq, dtype=torch.uint8, device=dev)
-        counts = torch.zeros(2, device=dev)
-        ops.seq_prep(tc, nseq, L, first_eos, visible, None, None, counts)
-        if pg is not None:
+        pre = getattr(h, "tgt_prep", None)
+        if pre is not None and pre["src"] is out["tgt_commands"] and pg is not None:
+            # SVGTransformer.forward already derived the target bookkeeping and started the global-count all-reduce
             import torch.distributed as dist
             world = dist.get_world_size(pg)
-            dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=pg)      # global masked counts
+            first_eos, visible, counts = pre["first_eos"], pre["visible"], pre["counts"]
+            pre["work"].wait()
+        else:
+            first_eos = torch.empty(nseq, dtype=torch.int32, device=dev)
+            visible = torch.empty(nseq, dtype=torch.uint8, device=dev)
+            counts = torch.zeros(2, device=dev)
+            ops.seq_prep(tc, nseq, L, first_eos, visible, None, None, counts)
+            if pg is not None:
+                import torch.distributed as dist
+                world = dist.get_world_size(pg)
+                dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=pg)      # global masked counts
         h.world = world
         acc = torch.zeros(8, device=dev)
         vals = torch.zeros(8, device=dev)
-        h.dl_args = Act(Md, na * C, planes, dev, ld=_r8(na * C))
-        h.dl_cmd = Act(Md, nc, planes, dev, ld=8)
+        bufs = getattr(h, "bufs", None)
+        h.dl_args = bufs["dl_args"] if bufs is not None else Act(Md, na * C, planes, dev, ld=_r8(na * C))
+        h.dl_cmd = bufs["dl_cmd"] if bufs is not None else Act(Md, nc, planes, dev, ld=8)
         ops.ce_args(al2, na * C, tc, ta, counts, h.dl_args, acc, nseq, L, na, C)
         ops.ce_cmd(cl2, tc, first_eos, visible, counts, h.dl_cmd, acc, nseq, L, nc)
         two = cfg.decode_stages == 2
         h.dl_vis = None
         if two:
             vl = out["visibility_logits"].detach().contiguous().view(nseq, 2)
-            h.dl_vis = Act(nseq, 2, planes, dev, ld=8)
+            h.dl_vis = bufs["dl_vis"] if bufs is not None else Act(nseq, 2, planes, dev, ld=8)
             ops.ce_vis(vl, visible, h.dl_vis, acc, nseq, 1.0 / (nseq * world))
         h.mu = h.ls = None
         has_kl = bool(cfg.use_vae)
@@ -146,7 +160,11 @@ class SVGLoss(nn.Module):
                           float(weights.get("loss_args_weight", 0.0)), float(weights.get("loss_visibility_weight", 0.0)),
                           float(weights.get("loss_kl_weight", 0.0)), float(weights.get("kl_tolerance", 0.0)),
                           1.0 / (nseq * world), 1.0 / (h.mu.numel() * world) if has_kl else 0.0, two, has_kl)
-        h.loss_out = vals
+        if bufs is not None:
+            bufs["loss_out"].copy_(vals)
+            h.loss_out = bufs["loss_out"]
+        else:
+            h.loss_out = vals
         return vals
 
     # -------------------------------------------------------------------------------------------------
@@ -167,7 +185,7 @@ class SVGLoss(nn.Module):
             vals = _FusedLoss.apply(self, handle, weights, output, handle.token, *logits)
         else:
             holder = _Holder()
-            holder.planes = 2
+            holder.planes = getattr(handle, "planes", 2) if handle is not None else 2
             vals = _StandaloneLoss.apply(self, holder, weights, output, *logits)
         res = {"loss": vals[0], "loss_cmd": vals[1], "loss_args": vals[2]}
         if two:

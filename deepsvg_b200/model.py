@@ -175,14 +175,17 @@ class LossHandle:
         self.scales = None
         self.loss_out = None
         self.used = False
+        self.bufs = None          # CUDA-graph mode: static buffers SVGLoss writes into (see _GraphState)
+        self.tgt_prep = None      # data-parallel mode: target bookkeeping + globally reduced counts, started before the forward
 
 
 class _SVGFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, inputs, token, *params):
         ctx.set_materialize_grads(False)
-        outs, saved = model._forward_impl(inputs)
+        outs, saved = model._run_forward(inputs)
         ctx.model, ctx.saved = model, saved
+        ctx.gen = getattr(saved, "gen", 0)
         saved.token = token
         ctx.n_outs = len(outs)
         return tuple(outs) + (token.detach().clone(),)
@@ -190,16 +193,25 @@ class _SVGFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *grads):
         model, saved = ctx.model, ctx.saved
-        flat = model._backward_impl(saved, grads[:-1], grads[-1])
+        flat = model._run_backward(saved, grads[:-1], grads[-1], ctx.gen)
         return (None, None, None) + tuple(flat)
 
 
 # ======================================================================================================
 class SVGTransformer(nn.Module):
-    def __init__(self, cfg, precision=None, process_group=None):
+    def __init__(self, cfg, precision=None, process_group=None, graphs=None):
         super().__init__()
         check_supported(cfg)
         self.cfg = cfg
+        # CUDA graphs: by default the train-mode step (forward; backward in two halves) is captured once the same input
+        # signature has been seen on three consecutive calls and replayed from then on (~400 kernel launches per step
+        # become three graph launches); graphs=False never captures.  Env DSVG_GRAPHS=0 / 1 sets the default.
+        if graphs is None:
+            graphs = os.environ.get("DSVG_GRAPHS", "1") != "0"
+        self.graphs = bool(graphs)
+        self._gs = None            # the one live _GraphState
+        self.graph_kernel_launches = 0   # kernels launched through graph replays (the library's own counter sees captures only)
+        self._gs_streak = (None, 0)
         self.args_dim = cfg.args_dim + 1                      # model.py:293 (rel_targets unsupported)
         self.precision = precision or os.environ.get("DSVG_PRECISION", "bf16")
         if self.precision not in ("bf16", "bf16x3"):
@@ -280,12 +292,16 @@ class SVGTransformer(nn.Module):
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in plist)
         token = torch.zeros((), device=ref.device, requires_grad=need_grad)
         need_grad = need_grad and not return_hierarch          # return_hierarch is an inference-only exit
+        inputs["need_grad"] = need_grad
+        tgt_prep = None
+        if need_grad and self.process_group is not None and return_tgt and commands_dec is not None and not encode_mode:
+            tgt_prep = self._prep_targets(commands_dec)
         if need_grad:
             outs = _SVGFunction.apply(self, inputs, token, *plist)
             outs, tok_out = outs[:-1], outs[-1]
         else:
             with torch.no_grad():
-                outs, _ = self._forward_impl(inputs)
+                outs, _ = self._run_forward(inputs)
             tok_out = None
         saved, self._last_saved = self._last_saved, None     # do not pin the activations on the module
         N = ref.shape[0]
@@ -311,10 +327,27 @@ class SVGTransformer(nn.Module):
         if tok_out is not None:
             handle = LossHandle(tok_out)
             handle.planes, handle.process_group = self.planes, self.process_group
+            handle.bufs = getattr(saved, "loss_bufs", None)     # graph mode: the loss writes into static buffers
+            handle.tgt_prep = tgt_prep
             saved.handle = handle
             for k in ("command_logits", "args_logits"):
                 res[k]._dsvg_handle = handle
         return res
+
+    def _prep_targets(self, commands_dec):
+        """Data-parallel runs: the masked-CE normalisers are GLOBAL counts (loss.py:53-54 under train.py:74).
+        They depend only on the targets, so their all-reduce is issued here, before the forward, on NCCL's own stream --
+        SVGLoss waits for it ~a forward pass later instead of stalling every rank in the middle of the step."""
+        import torch.distributed as dist
+        tc = commands_dec.detach().contiguous().float()
+        nseq, L = tc.shape[0] * tc.shape[1], tc.shape[2]
+        dev = tc.device
+        first_eos = torch.empty(nseq, dtype=torch.int32, device=dev)
+        visible = torch.empty(nseq, dtype=torch.uint8, device=dev)
+        counts = torch.zeros(2, device=dev)
+        ops.seq_prep(tc, nseq, L, first_eos, visible, None, None, counts)
+        work = dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=self.process_group, async_op=True)
+        return dict(src=commands_dec, tc=tc, first_eos=first_eos, visible=visible, counts=counts, work=work)
 
     # -------------------------------------------------------------------------------------------------
     # inference exit (SURVEY.md 8f rank 1): what cfg.visualize (default_icons.py:79-97), the notebooks and the GUI call
@@ -388,7 +421,8 @@ class SVGTransformer(nn.Module):
         """(p, site, seed) of a dropout call site; p = 0 in eval mode."""
         if not sv.training:
             return (0.0, 0, 0)
-        return (self.cfg.dropout if p is None else p, self._site(tag), sv.seed)
+        # bit 31 of the site: `seed` is a device pointer (include/dsvg_b200.h, DSVG_SEED_IS_DEVICE_PTR)
+        return (self.cfg.dropout if p is None else p, self._site(tag) | 0x80000000, sv.seed_ptr)
 
     def _layer_fwd(self, sv, pre, x, M, L, nseq, key_valid, rowvec, rpg):
         cfg = self.cfg
@@ -455,12 +489,19 @@ class SVGTransformer(nn.Module):
             x = self._layer_fwd(sv, lp, x, M, L, nseq, key_valid, rv, rpg)
         return x
 
-    def _forward_impl(self, inp):
+    def _forward_impl(self, inp, seed_dev=None):
         cfg = self.cfg
         sv = _Saved()
         self._last_saved = sv
         sv.training = bool(inp["training"])
-        sv.seed = int(torch.empty((), dtype=torch.int64).random_().item()) if sv.training else 0
+        sv.seed_dev, sv.seed_ptr = seed_dev, 0
+        if sv.training:
+            # the seed of this call's dropout masks lives in device memory (one uint64 per forward call, kept alive with the
+            # saved activations: the backward regenerates the masks from it); drawn from torch's CUDA generator
+            if seed_dev is None:
+                ref = inp["commands"] if inp["commands"] is not None else inp["z"]
+                sv.seed_dev = torch.empty(1, dtype=torch.int64, device=ref.device).random_()
+            sv.seed_ptr = sv.seed_dev.data_ptr()
         d, dz = cfg.d_model, cfg.dim_z
         two = cfg.encode_stages == 2
         pl = self.planes
@@ -728,7 +769,18 @@ class SVGTransformer(nn.Module):
             ops.outer(dl, y, M, n_out, d, gd[name + ".weight"], alpha_dev=sc, colsum=gd[name + ".bias"])
             ops.linear(dl, wt, M, d, n_out, acc_scale=sc, residual=dy32, out_f32=dy32)
 
-    def _backward_impl(self, sv, out_grads, g_token):
+    def _bucket_split(self):
+        """Offset (in elements) of the first decoder parameter in the flat gradient bucket.  The decoder half of the backward
+        (heads, D1, D2) completes exactly flat[split:]; the encoder half (latent, E2, E1, embedding) completes flat[:split]."""
+        off = 0
+        for n in self._pnames:
+            if n.startswith("decoder."):
+                return off
+            off += self._param(n).numel()
+        return off
+
+    def _backward_a(self, sv, out_grads, g_token):
+        """Decoder half of the backward pass (output heads, D1, D2).  Returns the state the encoder half continues from."""
         cfg = self.cfg
         d, dz = cfg.d_model, cfg.dim_z
         two = cfg.encode_stages == 2
@@ -822,7 +874,18 @@ class SVGTransformer(nn.Module):
                                    self._drop(sv, "dec.pe2", 0.1))
             if cfg.label_condition:
                 ops.scatter_rows(dlab_d, sv.label, N, cfg.dim_label, gd["decoder.label_embedding.label_embedding.weight"])
+        return dict(flat=flat, gd=gd, dz32=dz32, dmu_ext=dmu_ext, dls_ext=dls_ext, fused=fused, handle=handle)
 
+    def _backward_b(self, sv, st):
+        """Encoder half of the backward pass: latent block, E2, E1, embedding."""
+        cfg = self.cfg
+        d, dz = cfg.d_model, cfg.dim_z
+        two = cfg.encode_stages == 2
+        pl = self.planes
+        P = self._param
+        gd, dz32, dmu_ext, dls_ext, fused, handle = st["gd"], st["dz32"], st["dmu_ext"], st["dls_ext"], st["fused"], st["handle"]
+        dev = dz32.device
+        N = sv.N
         if sv.has_encoder:
             # ---- latent (model.py:361-367) ----
             dzin = torch.zeros(N, d, device=dev)        # grad w.r.t. the ResNet output
@@ -887,9 +950,186 @@ class SVGTransformer(nn.Module):
             if cfg.label_condition:
                 ops.scatter_rows(dlab_e, sv.label, N, cfg.dim_label, gd["encoder.label_embedding.label_embedding.weight"])
 
-        if self.process_group is not None:
+    # =================================================================================================
+    # step execution: eager launches, or CUDA-graph replay of the captured launch sequences
+    # =================================================================================================
+    def _graph_key(self, inp):
+        """Input signature a captured graph is valid for, or None when this call is not graphable."""
+        if not self.graphs or not inp["training"] or not inp.get("need_grad", False) or inp["z"] is not None \
+                or inp["encode_mode"] or inp["return_hierarch"] or ops.PROFILE is not None:
+            return None
+        c, a, lab = inp["commands"], inp["args"], inp["label"]
+        if c.dtype != torch.float32 or a.dtype != torch.float32:
+            return None
+        if self._eps_override is not None:          # injected VAE noise (tests): a caller-owned tensor, not capturable
+            return None
+        ptrs = tuple(self._param(n).data_ptr() for n in self._pnames)
+        return (tuple(c.shape), tuple(a.shape), None if lab is None else tuple(lab.shape), str(c.device), self.planes,
+                hash(ptrs))
+
+    def release_graphs(self):
+        """Drops the captured step (and its private memory pool: activations of one step)."""
+        gs, self._gs = self._gs, None
+        self._gs_streak = (None, 0)
+        if gs is not None:
+            gs.release()
+
+    def _refresh_weights(self):
+        """Re-cast every cached bf16 weight operand whose fp32 master changed (eager launches, outside the graphs)."""
+        for name, dev in list(self._wcache):
+            self._pack(name)
+
+    def _run_forward(self, inp):
+        key = self._graph_key(inp)
+        gs = self._gs
+        if key is None:
+            return self._forward_impl(inp)
+        if gs is not None and gs.key == key:
+            return gs.replay_forward(inp)
+        last, n = self._gs_streak
+        n = n + 1 if last == key else 1
+        self._gs_streak = (key, n)
+        if n < 3:
+            return self._forward_impl(inp)                      # warm-up: eager (also fills the weight-operand cache)
+        if gs is not None:
+            self._gs = None
+            gs.release()
+        try:
+            gs = _GraphState(self, key, inp)
+        except Exception as e:                                   # capture is an optimisation: fall back to eager launches
+            import sys
+            sys.stderr.write("deepsvg_b200: WARNING: CUDA-graph capture of the forward failed (%r); running eagerly\n" % (e,))
+            self.graphs = False
+            return self._forward_impl(inp)
+        self._gs = gs
+        return gs.replay_forward(inp)
+
+    def _run_backward(self, sv, out_grads, g_token, gen):
+        gs = getattr(sv, "graph", None)
+        if gs is not None and gen != gs.gen:
+            raise RuntimeError("deepsvg_b200: backward() of an earlier forward after a later one overwrote the captured "
+                               "activations (CUDA-graph mode keeps ONE set of activation buffers); construct "
+                               "SVGTransformer(..., graphs=False) for this usage")
+        handle = getattr(sv, "handle", None)
+        fused_only = (g_token is not None and handle is not None and handle.dl_args is not None
+                      and all(g is None for g in out_grads))
+        pg = self.process_group
+        if gs is not None and fused_only and handle.bufs is gs.loss_bufs and gs.backward_ok:
+            return gs.replay_backward(sv, out_grads, g_token)
+        st = self._backward_a(sv, out_grads, g_token)
+        flat, gd = st["flat"], st["gd"]
+        work = None
+        if pg is not None:
             import torch.distributed as dist
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.process_group)   # the ONE data-path collective
-        sv.layers.clear()
-        sv.__dict__.clear()     # release all saved activations now (the autograd node may outlive this call)
-        return [gd[n] for n in self._pnames]
+            split = self._bucket_split()
+            # decoder gradients are final: their all-reduce runs on NCCL's stream while the encoder half computes
+            work = dist.all_reduce(flat[split:], op=dist.ReduceOp.SUM, group=pg, async_op=True)
+        self._backward_b(sv, st)
+        if pg is not None:
+            dist.all_reduce(flat[:split], op=dist.ReduceOp.SUM, group=pg)
+            work.wait()
+        if gs is None:
+            sv.layers.clear()
+            sv.__dict__.clear()     # release all saved activations now (the autograd node may outlive this call)
+            return [gd[n] for n in self._pnames]
+        return [g.clone() for g in (gd[n] for n in self._pnames)]
+
+
+class _GraphState:
+    """One captured train step: static input buffers, the forward graph, the two backward graphs (decoder half / encoder
+    half, so that the gradient all-reduce of the decoder half overlaps the encoder half), and the saved-activation record
+    whose tensors live in the graphs' private memory pool.  Outputs and activations are overwritten by every replay."""
+
+    def __init__(self, model, key, inp):
+        self.model, self.key = model, key
+        self.gen = 0
+        c, a, lab = inp["commands"], inp["args"], inp["label"]
+        dev = c.device
+        self.cmd, self.args = c.detach().clone().contiguous(), a.detach().clone().contiguous()
+        self.label = lab.detach().clone() if lab is not None else None
+        self.seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)     # redrawn before every replay
+        self.pool = torch.cuda.graph_pool_handle()
+        self.bwd_a = self.bwd_b = None
+        self.backward_ok = True
+        self.bst = None
+        model._refresh_weights()
+        static = dict(inp, commands=self.cmd, args=self.args, label=self.label)
+        torch.cuda.synchronize(dev)
+        self.fwd = torch.cuda.CUDAGraph()
+        from . import _lib
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(self.fwd, pool=self.pool):
+            outs, sv = model._forward_impl(static, seed_dev=self.seed_dev)
+        self.n_fwd, self.n_bwd = _lib.launch_count() - n0, 0      # kernel nodes per replay
+        self.outs, self.sv = outs, sv
+        sv.graph = self
+        # static buffers SVGLoss writes its outputs into (the backward graphs read them)
+        cfg = model.cfg
+        two = cfg.decode_stages == 2
+        Md, nseq_d = sv.Md, sv.nseq_d
+        na_out, nc = cfg.n_args * model.args_dim, cfg.n_commands
+        pl = model.planes
+        self.loss_bufs = dict(dl_args=Act(Md, na_out, pl, dev, ld=_r8(na_out)), dl_cmd=Act(Md, nc, pl, dev, ld=8),
+                              dl_vis=Act(nseq_d, 2, pl, dev, ld=8) if two else None,
+                              scales=torch.zeros(4, device=dev), loss_out=torch.zeros(8, device=dev))
+        sv.loss_bufs = self.loss_bufs
+
+    def release(self):
+        self.fwd = self.bwd_a = self.bwd_b = None
+        self.outs = self.sv = self.bst = self.loss_bufs = None
+
+    def replay_forward(self, inp):
+        m = self.model
+        self.cmd.copy_(inp["commands"], non_blocking=True)
+        self.args.copy_(inp["args"], non_blocking=True)
+        if self.label is not None:
+            self.label.copy_(inp["label"], non_blocking=True)
+        self.seed_dev.random_()
+        m._refresh_weights()
+        self.fwd.replay()
+        m.graph_kernel_launches += self.n_fwd
+        self.gen += 1
+        self.sv.gen = self.gen
+        m._last_saved = self.sv
+        return [t.detach() for t in self.outs], self.sv
+
+    def replay_backward(self, sv, out_grads, g_token):
+        m = self.model
+        if self.bwd_a is None:
+            try:
+                torch.cuda.synchronize()
+                ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                from . import _lib
+                n0 = _lib.launch_count()
+                with torch.cuda.graph(ga, pool=self.pool):
+                    st = m._backward_a(sv, out_grads, g_token)
+                with torch.cuda.graph(gb, pool=self.pool):
+                    m._backward_b(sv, st)
+                self.n_bwd = _lib.launch_count() - n0
+                self.bwd_a, self.bwd_b, self.bst = ga, gb, st
+            except Exception as e:
+                import sys
+                sys.stderr.write("deepsvg_b200: WARNING: CUDA-graph capture of the backward failed (%r); the backward runs "
+                                 "eagerly\n" % (e,))
+                self.backward_ok = False
+                return m._run_backward(sv, out_grads, g_token, self.gen)
+        flat, gd = self.bst["flat"], self.bst["gd"]
+        pg = m.process_group
+        self.bwd_a.replay()
+        m.graph_kernel_launches += self.n_bwd
+        work = None
+        if pg is not None:
+            import torch.distributed as dist
+            split = m._bucket_split()
+            work = dist.all_reduce(flat[split:], op=dist.ReduceOp.SUM, group=pg, async_op=True)
+        self.bwd_b.replay()
+        if pg is not None:
+            dist.all_reduce(flat[:split], op=dist.ReduceOp.SUM, group=pg)
+            work.wait()
+        out = flat.clone()          # p.grad must not alias the buffer the next replay overwrites
+        res, off = [], 0
+        for n in m._pnames:
+            p = m._param(n)
+            res.append(out[off:off + p.numel()].view(p.shape))
+            off += p.numel()
+        return res

@@ -12,12 +12,16 @@
  *   - "act" tensors are bf16 with an optional second "lo" plane `lo_off` ELEMENTS after the first
  *     (lo_off = 0: fast single-plane bf16; lo_off != 0: parity mode, value = hi + lo, GEMMs run as bf16x3);
  *   - dropout masks come from a stateless counter hash keyed by (seed, site, element index); p = 0 disables it
- *     (eval mode); the backward pass regenerates the forward mask from the same triple.
+ *     (eval mode); the backward pass regenerates the forward mask from the same triple.  If bit 31 of `drop_site`
+ *     (DSVG_SEED_IS_DEVICE_PTR) is set, `seed` is not the seed itself but a DEVICE POINTER to a uint64 holding it, read by
+ *     the kernel at run time: a captured CUDA graph then draws fresh masks on every replay (the caller rewrites the
+ *     uint64 between replays).
  */
 #ifndef DSVG_B200_H
 #define DSVG_B200_H
 
 #include <stddef.h>
+#define DSVG_SEED_IS_DEVICE_PTR 0x80000000u
 #include <stdint.h>
 
 #ifdef __cplusplus

@@ -293,7 +293,8 @@ def test_fused_adamw_updates_reach_the_gemm_weights():
     moved = (logits[0][1] - logits[0][0]).abs().max().item()
     assert moved > 1e-3, "the second forward did not see the optimizer update (stale weight cache)"
     for s in (1, 2):
-        np.testing.assert_allclose(logits[0][s].cpu().numpy(), logits[1][s].cpu().numpy(), rtol=2e-3, atol=2e-4)
+        # two different (both correct) AdamW / clipping implementations: agreement to a few 1e-4 after lr = 3e-3 updates
+        np.testing.assert_allclose(logits[0][s].cpu().numpy(), logits[1][s].cpu().numpy(), rtol=5e-3, atol=2e-3)
 
 
 def test_parity_mode_at_the_benchmarked_shape():
@@ -340,3 +341,85 @@ def test_nccl_data_parallel_gradients_match_single_process():
     line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     chk = line["ddp_check"]
     assert chk["max_rel_grad_err"] < 1e-3 and chk["rel_loss_err"] < 1e-5, chk
+
+
+# ------------------------------------------------------------------------------------------------ CUDA graphs
+def _train_pair(cfg, n=6, seed=3):
+    from deepsvg_b200 import SVGLoss, SVGTransformer
+    from deepsvg_b200.config import _DefaultConfig
+    c = _DefaultConfig(**{k: v for k, v in vars(cfg).items()})
+    params = O.make_params(cfg, seed=seed)
+    models = []
+    for g in (True, False):
+        m = SVGTransformer(c, precision="bf16", graphs=g)
+        m.load_state_dict(params, strict=False)
+        models.append(m.to(DEV).train())
+    return models, SVGLoss(c).to(DEV)
+
+
+def test_cuda_graph_step_matches_eager_step():
+    """Train mode, dropout on: from the third call with the same input signature the step is three graph replays.  With
+    the same torch CUDA seed both paths draw the same dropout seed, so loss and gradients must agree (fp32 atomics in the
+    weight-gradient reductions are the only non-determinism)."""
+    cfg = O.make_cfg("hierarchical", use_vae=False, d_model=128, n_heads=4, dim_feedforward=256, dim_z=64, n_layers=2,
+                     n_layers_decode=2, max_num_groups=4, max_seq_len=10)
+    (mg, me), loss_fn = _train_pair(cfg)
+    batches = [O.synth_batch(cfg, 6, seed=40 + i) for i in range(6)]
+    for i, (cmd, arg) in enumerate(batches):
+        c, a = cmd.to(DEV), arg.to(DEV)
+        res = []
+        for m in (mg, me):
+            torch.manual_seed(1000 + i)
+            m.zero_grad(set_to_none=True)
+            out = m(c, a, c, a, params={})
+            ls = loss_fn(out, None, weights=W)
+            ls["loss"].backward()
+            res.append((ls["loss"].item(), out["args_logits"].detach().clone(),
+                        {k: p.grad.detach().clone() for k, p in m.named_parameters()}))
+        assert (mg._gs is not None) == (i >= 2), i
+        assert abs(res[0][0] - res[1][0]) < 1e-5 * abs(res[1][0]), (i, res[0][0], res[1][0])
+        assert torch.allclose(res[0][1], res[1][1], rtol=1e-5, atol=1e-6), i
+        for k, g in res[1][2].items():
+            e = (res[0][2][k] - g).norm().item() / (g.norm().item() + 1e-12)
+            assert e < 1e-4, (i, k, e)
+    assert me._gs is None
+    # different dropout masks on consecutive replays (the seed lives in device memory)
+    c, a = batches[0][0].to(DEV), batches[0][1].to(DEV)
+    o1 = mg(c, a, c, a, params={})["args_logits"].clone()
+    o2 = mg(c, a, c, a, params={})["args_logits"].clone()
+    assert not torch.equal(o1, o2)
+
+
+def test_cuda_graph_guards_and_optimizer_updates():
+    """(a) backward of an earlier forward after a later replay must raise (one activation set); (b) FusedAdamW updates
+    reach the captured graphs (weights are re-cast outside the graph when their version changes); (c) a new input
+    signature drops the old capture."""
+    from deepsvg_b200 import FusedAdamW
+    cfg = O.make_cfg("hierarchical", use_vae=True, d_model=128, n_heads=4, dim_feedforward=256, dim_z=64, n_layers=2,
+                     n_layers_decode=2, max_num_groups=4, max_seq_len=10)
+    (mg, me), loss_fn = _train_pair(cfg)
+    cmd, arg = O.synth_batch(cfg, 5, seed=9)
+    c, a = cmd.to(DEV), arg.to(DEV)
+    opt = FusedAdamW(mg.parameters(), lr=2e-3, max_grad_norm=1.0)
+    losses = []
+    for i in range(12):
+        mg.zero_grad(set_to_none=True)
+        ls = loss_fn(mg(c, a, c, a, params={}), None, weights=W)
+        ls["loss"].backward()
+        assert all(torch.isfinite(p.grad).all() for p in mg.parameters())
+        opt.step()
+        losses.append(ls["loss_args"].item() + ls["loss_cmd"].item())
+    assert mg._gs is not None and mg._gs.bwd_a is not None
+    assert losses[-1] < losses[2] - 0.05, losses          # it learns: the replays see the updated weights
+    o1 = mg(c, a, c, a, params={})
+    l1 = loss_fn(o1, None, weights=W)["loss"]
+    o2 = mg(c, a, c, a, params={})
+    with pytest.raises(RuntimeError, match="overwrote the captured"):
+        l1.backward()
+    gs = mg._gs
+    cmd2, arg2 = O.synth_batch(cfg, 3, seed=10)
+    c2, a2 = cmd2.to(DEV), arg2.to(DEV)
+    for _ in range(3):
+        mg.zero_grad(set_to_none=True)
+        loss_fn(mg(c2, a2, c2, a2, params={}), None, weights=W)["loss"].backward()
+    assert mg._gs is not None and mg._gs is not gs and mg._gs.key != gs.key
