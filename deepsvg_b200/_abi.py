@@ -19,6 +19,9 @@ SIGNATURES = {
     "dsvg_abi_version": (I, []),
     "dsvg_linear": (I, [P, Z, I, P, Z, I, I, I, I, P, P]),
     "dsvg_outer": (I, [P, Z, I, P, Z, I, I, I, I, F, P, P, I, P, P]),
+    "dsvg_linear_ln_fusable": (I, [I, I, I]),
+    "dsvg_linear_ln_fwd": (I, [P, Z, I, P, Z, I, I, I, I, P, P, P, P, P, P, P]),
+    "dsvg_linear_ln_bwd": (I, [P, Z, I, P, Z, I, I, I, I, P, P, P, P, P, P, P] + DROP + [P, P, P]),
     "dsvg_seq_prep": (I, [P, I, I, P, P, P, P, P, P]),
     "dsvg_embed_fold": (I, [P, P, P, P, P, I, I, I, P]),
     "dsvg_embed_fwd": (I, [P, P, P, P, P, P, P, P, P, I, I, I, I, I] + DROP + [P]),

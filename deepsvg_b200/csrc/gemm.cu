@@ -145,7 +145,21 @@ struct Epi {
   size_t out_lo_off;
   int out_act_ld;
   int vec;   // 1: every pointer/stride satisfies the 4-wide vector path
-  int mode;  // 0: generic run-time epilogue; k > 0: lean epilogue kLeanFeat[k - 1]
+  int mode;  // 0: generic run-time epilogue; k > 0: lean epilogue kLeanFeat[k - 1]; 8 / 9: fused LayerNorm (see below)
+  // ---- fused LayerNorm (N == BN == 256: a CTA tile owns whole rows) ----
+  // mode 8 (forward):  x1 = residual epilogue of mode 4 -> out_f32;  ln_out = bf16(LN(x1) * gamma + beta); stats saved
+  // mode 9 (backward): dy = accumulator (dgrad into the LN output); dx_out = LN'(dy; x, mean, rstd, gamma) + dx_in;
+  //                    dact = bf16(dropout_mask * dx_out); dgamma / dbeta accumulated
+  const float* ln_gamma;
+  const float* ln_beta;
+  bf16* ln_out;         // mode 8: [M, 256] ; mode 9: dact or null
+  float* ln_mean;       // mode 8: written ; mode 9: read
+  float* ln_rstd;
+  const float* ln_x;    // mode 9: the LayerNorm input (fp32 residual stream), row stride 256
+  const float* ln_dx_in;
+  float* ln_dx_out;
+  float* ln_dgamma;
+  float* ln_dbeta;
   long long* dbg;  // development trace (dsvg_debug_linear_trace): per-tile clock64 stamps of CTA 0, or null
 };
 
@@ -477,6 +491,21 @@ __device__ __forceinline__ void epilogue_chunk_lean(uint32_t (&v)[32], uint32_t 
   __syncwarp();
 }
 
+// sum over the 8 lanes that share a row group (lane bits 0..2 = column group)
+__device__ __forceinline__ float sum_cg(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  return v;
+}
+__device__ __forceinline__ void st_bf16x4(bf16* p, float a, float b, float c, float d) {
+  __nv_bfloat162 h0 = __floats2bfloat162_rn(a, b), h1 = __floats2bfloat162_rn(c, d);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&h0);
+  u.y = *reinterpret_cast<uint32_t*>(&h1);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
 // feature sets with a compiled lean epilogue (index = Epi::mode - 1)
 constexpr uint32_t kLeanFeat[] = {
     F_OUTA,                                   // 1: plain dgrad
@@ -607,7 +636,7 @@ __device__ __forceinline__ void tma_out_load_mask(uint4 (&mk)[4], long long grow
 __host__ __device__ constexpr int lin_epi_warps(int mode, int bn) {
   // the fp32-residual epilogues (modes 4, 6) are stall-bound chains of shared / global accesses with no single hot
   // spot (ncu: issue slots 29 % busy with 2 warps per scheduler): the 256-wide, one-CTA-per-SM kernel runs them 16 wide
-  return ((mode >= 3 && mode <= 7) && bn == 256) ? 16 : 8;
+  return ((mode >= 3 && mode <= 9) && bn == 256) ? 16 : 8;
 }
 // act-output lean modes write their bf16 tile through shared memory with one TMA store per 64-column box
 __host__ __device__ constexpr bool lin_tma_out(int mode) { return mode == 1 || mode == 2 || mode == 3 || mode == 5; }
@@ -632,7 +661,9 @@ struct LinearCfg {
   static_assert(kStages >= 2, "linear: at least two pipeline stages must fit");
   static constexpr int kTmemCols = 2 * BN;  // two accumulator stages (256 or 512: powers of two)
   static constexpr int kBiasBytes = BN * 4;   // bias slice of the current n-tile (TMA-out epilogues)
-  static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kStagingBytes + 256 + kBiasBytes;
+  // fused LayerNorm: row partials [2 tile parities][128 rows][4 column quarters][2] + per-CTA dgamma / dbeta [2][256]
+  static constexpr int kLnBytes = (MODE == 8 || MODE == 9) ? (2 * 128 * 4 * 2 * 4 + 2 * 256 * 4) : 0;
+  static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kStagingBytes + 256 + kBiasBytes + kLnBytes;
 };
 
 template <int BN, int NPLANES, int MODE>
@@ -653,6 +684,8 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   uint64_t* tempty_bar = tfull_bar + 2;            // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* bias_sm = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kStagingBytes + 256);
+  float* ln_part = bias_sm + BN;              // modes 8 / 9 only (Cfg::kLnBytes)
+  float* ln_acc = ln_part + 2 * 128 * 4 * 2;  // mode 9: [2][256] dgamma / dbeta of this CTA
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -769,6 +802,10 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   } else {
     // =================== epilogue warps (2 .. 2 + kEpiWarps) ===================
     drop_resolve(ep.drop);
+    if constexpr (MODE == 9) {
+      for (int j = threadIdx.x - 64; j < 512; j += Cfg::kEpiWarps * 32) ln_acc[j] = 0.f;
+      named_bar_sync(2, Cfg::kEpiWarps * 32);
+    }
     const int quarter = warp & 3;         // TMEM lane quarter this warp may read
     const int half = (warp - 2) >> 2;     // which 32-column chunk of every kCols-wide pass this warp drains
     const uint32_t stage_buf = smem_u32(staging) + (warp - 2) * kStageWarpBytes;
@@ -858,6 +895,301 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         }
         if (warp == 2) trace_stamp(ep, it, 12, lane);
         continue;
+      } else if constexpr (MODE == 8) {
+        // ---------------- residual epilogue (as mode 4) + LayerNorm of the finished rows ----------------
+        static_assert(BN == 256 && kCols == 128, "fused LayerNorm needs whole rows per CTA tile");
+        const int cg = lane & 7, rsub = lane >> 3;
+        const int r_first = int(row0) + rsub;
+        float* part = ln_part + (it & 1) * (128 * 4 * 2);
+        const bool has_rv = ep.rowvec != nullptr, has_drop = ep.drop.p > 0.f, has_res = ep.residual != nullptr;
+        float rs[8], rq[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rs[i] = rq[i] = 0.f;
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci) {
+          const int c = half * 32 + kCols * ci;
+          const int col = n0 + c + 4 * cg;
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * BN + c), v);
+          const float4 bias4 = ep.bias != nullptr ? __ldg(reinterpret_cast<const float4*>(ep.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          tmem_ld_wait();
+          {
+            const uint32_t my = stage_buf + lane * (kStageRow * 4);
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              st_shared_v4(my + q * 16, __uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                           __uint_as_float(v[4 * q + 3]));
+          }
+          __syncwarp();
+          const uint32_t lds_base = stage_buf + (rsub * kStageRow + 4 * cg) * 4;
+          const unsigned long long quad0 = ((unsigned long long)r_first * 256ull + (unsigned long long)col) >> 2;
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {                  // four rows at a time: their residual loads fly together
+            float4 res[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int row = r_first + 4 * (4 * hh + k);
+              res[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (row < M && has_res) res[k] = *reinterpret_cast<const float4*>(ep.residual + size_t(row) * ep.res_ld + col);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int i = 4 * hh + k;
+              const int row = r_first + 4 * i;
+              float4 x = ld_shared_v4(lds_base + i * (4 * kStageRow * 4));
+              if (row < M) {
+                x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w;
+                if (has_drop) {
+                  const unsigned long long quad = quad0 + (unsigned long long)i * 256ull;   // row advances by 4
+                  const float4 m = dropout_quad_mult(ep.drop, uint32_t(quad), drop_hikey(ep.drop, quad));
+                  x.x *= m.x; x.y *= m.y; x.z *= m.z; x.w *= m.w;
+                }
+                if (has_rv) {
+                  const uint32_t grp = ep.rpg_magic ? __umulhi(uint32_t(row), ep.rpg_magic) : uint32_t(row / ep.rows_per_group);
+                  const float4 rv = __ldg(reinterpret_cast<const float4*>(ep.rowvec + size_t(grp) * ep.rowvec_ld + col));
+                  x.x += rv.x; x.y += rv.y; x.z += rv.z; x.w += rv.w;
+                }
+                x.x += res[k].x; x.y += res[k].y; x.z += res[k].z; x.w += res[k].w;
+                *reinterpret_cast<float4*>(ep.out_f32 + size_t(row) * ep.out_f32_ld + col) = x;
+                rs[i] += (x.x + x.y) + (x.z + x.w);
+                rq[i] += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
+              }
+            }
+          }
+          __syncwarp();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);     // accumulator consumed: the MMA warp may reuse this TMEM stage
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          rs[i] = sum_cg(rs[i]);
+          rq[i] = sum_cg(rq[i]);
+        }
+        if (cg == 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float2* dst = reinterpret_cast<float2*>(part + ((quarter * 32 + rsub + 4 * i) * 4 + half) * 2);
+            *dst = make_float2(rs[i], rq[i]);
+          }
+        }
+        named_bar_sync(3 + quarter, 128);                 // the four warps that share these 32 rows
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {                     // rs <- mean, rq <- rstd
+          const float4* src = reinterpret_cast<const float4*>(part + (quarter * 32 + rsub + 4 * i) * 8);
+          const float4 p0 = src[0], p1 = src[1];          // (s, q) of column quarters 0, 1 | 2, 3
+          const float sm = (p0.x + p0.z) + (p1.x + p1.z), sq = (p0.y + p0.w) + (p1.y + p1.w);
+          rs[i] = sm * (1.f / 256.f);
+          rq[i] = rsqrtf(fmaxf(sq * (1.f / 256.f) - rs[i] * rs[i], 0.f) + 1e-5f);
+        }
+        if (half == 0 && cg == 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = r_first + 4 * i;
+            if (row < M) {
+              ep.ln_mean[row] = rs[i];
+              ep.ln_rstd[row] = rq[i];
+            }
+          }
+        }
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci) {
+          const int col = n0 + half * 32 + kCols * ci + 4 * cg;
+          const float4 g4 = __ldg(reinterpret_cast<const float4*>(ep.ln_gamma + col));
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.ln_beta + col));
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            float4 xv[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {                 // this lane's own stores of phase 1 (L2 hits)
+              const int row = r_first + 4 * (4 * hh + k);
+              if (row < M) xv[k] = *reinterpret_cast<const float4*>(ep.out_f32 + size_t(row) * ep.out_f32_ld + col);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int i = 4 * hh + k;
+              const int row = r_first + 4 * i;
+              const float sc = rq[i], sh = -rs[i] * rq[i];   // (x - mean) rstd = x sc + sh
+              if (row < M)
+                st_bf16x4(ep.ln_out + size_t(row) * 256 + col, (xv[k].x * sc + sh) * g4.x + b4.x, (xv[k].y * sc + sh) * g4.y + b4.y,
+                          (xv[k].z * sc + sh) * g4.z + b4.z, (xv[k].w * sc + sh) * g4.w + b4.w);
+            }
+          }
+        }
+        continue;
+      } else if constexpr (MODE == 9) {
+        // ---------------- dgrad into a LayerNorm output + the LayerNorm backward of the finished rows ----------------
+        static_assert(BN == 256 && kCols == 128, "fused LayerNorm needs whole rows per CTA tile");
+        const int cg = lane & 7, rsub = lane >> 3;
+        float* part = ln_part + (it & 1) * (128 * 4 * 2);
+        float mean[8], rstd[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = int(row0) + rsub + 4 * i;
+          mean[i] = row < M ? __ldg(ep.ln_mean + row) : 0.f;
+          rstd[i] = row < M ? __ldg(ep.ln_rstd + row) : 0.f;
+        }
+        float4 g4[2];
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci)
+          g4[ci] = __ldg(reinterpret_cast<const float4*>(ep.ln_gamma + n0 + half * 32 + kCols * ci + 4 * cg));
+        float s1[8], s2[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
+        float4 xv[8];
+        {
+          const int col = n0 + half * 32 + 4 * cg;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = int(row0) + rsub + 4 * i;
+            if (row < M) xv[i] = *reinterpret_cast<const float4*>(ep.ln_x + size_t(row) * 256 + col);
+          }
+        }
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        // phase 1: row sums  s1 = sum_j dy_j g_j,  s2 = sum_j dy_j g_j xhat_j;  column sums for dgamma / dbeta
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci) {
+          const int c = half * 32 + kCols * ci;
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * BN + c), v);
+          tmem_ld_wait();
+          {
+            const uint32_t my = stage_buf + lane * (kStageRow * 4);
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              st_shared_v4(my + q * 16, __uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                           __uint_as_float(v[4 * q + 3]));
+          }
+          __syncwarp();
+          const uint32_t lds_base = stage_buf + (rsub * kStageRow + 4 * cg) * 4;
+          float4 dgc = make_float4(0.f, 0.f, 0.f, 0.f), dbc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = int(row0) + rsub + 4 * i;
+            const float4 dy = ld_shared_v4(lds_base + i * (4 * kStageRow * 4));
+            if (row < M) {
+              const float4 xh = make_float4((xv[i].x - mean[i]) * rstd[i], (xv[i].y - mean[i]) * rstd[i],
+                                            (xv[i].z - mean[i]) * rstd[i], (xv[i].w - mean[i]) * rstd[i]);
+              const float4 t = make_float4(dy.x * g4[ci].x, dy.y * g4[ci].y, dy.z * g4[ci].z, dy.w * g4[ci].w);
+              s1[i] += (t.x + t.y) + (t.z + t.w);
+              s2[i] += (t.x * xh.x + t.y * xh.y) + (t.z * xh.z + t.w * xh.w);
+              dgc.x += dy.x * xh.x; dgc.y += dy.y * xh.y; dgc.z += dy.z * xh.z; dgc.w += dy.w * xh.w;
+              dbc.x += dy.x; dbc.y += dy.y; dbc.z += dy.z; dbc.w += dy.w;
+            }
+          }
+          __syncwarp();
+          // the 4 row groups of this warp share the lane's columns: fold them, then one shared-memory atomic per column
+          dgc.x += __shfl_xor_sync(0xffffffffu, dgc.x, 8); dgc.y += __shfl_xor_sync(0xffffffffu, dgc.y, 8);
+          dgc.z += __shfl_xor_sync(0xffffffffu, dgc.z, 8); dgc.w += __shfl_xor_sync(0xffffffffu, dgc.w, 8);
+          dbc.x += __shfl_xor_sync(0xffffffffu, dbc.x, 8); dbc.y += __shfl_xor_sync(0xffffffffu, dbc.y, 8);
+          dbc.z += __shfl_xor_sync(0xffffffffu, dbc.z, 8); dbc.w += __shfl_xor_sync(0xffffffffu, dbc.w, 8);
+          dgc.x += __shfl_xor_sync(0xffffffffu, dgc.x, 16); dgc.y += __shfl_xor_sync(0xffffffffu, dgc.y, 16);
+          dgc.z += __shfl_xor_sync(0xffffffffu, dgc.z, 16); dgc.w += __shfl_xor_sync(0xffffffffu, dgc.w, 16);
+          dbc.x += __shfl_xor_sync(0xffffffffu, dbc.x, 16); dbc.y += __shfl_xor_sync(0xffffffffu, dbc.y, 16);
+          dbc.z += __shfl_xor_sync(0xffffffffu, dbc.z, 16); dbc.w += __shfl_xor_sync(0xffffffffu, dbc.w, 16);
+          if (rsub == 0) {
+            float* ag = ln_acc + c + 4 * cg;
+            atomicAdd(ag + 0, dgc.x); atomicAdd(ag + 1, dgc.y); atomicAdd(ag + 2, dgc.z); atomicAdd(ag + 3, dgc.w);
+            atomicAdd(ag + 256, dbc.x); atomicAdd(ag + 257, dbc.y); atomicAdd(ag + 258, dbc.z); atomicAdd(ag + 259, dbc.w);
+          }
+          if (ci == 0) {
+            const int col = n0 + c + kCols + 4 * cg;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int row = int(row0) + rsub + 4 * i;
+              if (row < M) xv[i] = *reinterpret_cast<const float4*>(ep.ln_x + size_t(row) * 256 + col);
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s1[i] = sum_cg(s1[i]);
+          s2[i] = sum_cg(s2[i]);
+        }
+        if (cg == 0) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float2* dst = reinterpret_cast<float2*>(part + ((quarter * 32 + rsub + 4 * i) * 4 + half) * 2);
+            *dst = make_float2(s1[i], s2[i]);
+          }
+        }
+        named_bar_sync(3 + quarter, 128);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4* src = reinterpret_cast<const float4*>(part + (quarter * 32 + rsub + 4 * i) * 8);
+          const float4 p0 = src[0], p1 = src[1];
+          const float c1 = ((p0.x + p0.z) + (p1.x + p1.z)) * (1.f / 256.f);
+          const float c2 = ((p0.y + p0.w) + (p1.y + p1.w)) * (1.f / 256.f);
+          // dx = r (dy g - c1 - xhat c2) = dy (r g) + x B + C   with  B = -r^2 c2,  C = -r c1 + mean r^2 c2
+          const float r = rstd[i];
+          s2[i] = -r * r * c2;
+          s1[i] = -r * c1 - mean[i] * s2[i];
+        }
+        // phase 2: dx = rstd * (dy g - s1 - xhat s2) + dx_in  (second pass over the accumulator, x re-read from L2)
+        const bool has_drop = ep.drop.p > 0.f;
+#pragma unroll
+        for (int ci = 1; ci >= 0; --ci) {                 // xv still holds the columns of pass 1
+          const int c = half * 32 + kCols * ci;
+          const int col = n0 + c + 4 * cg;
+          if (ci == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int row = int(row0) + rsub + 4 * i;
+              if (row < M) xv[i] = *reinterpret_cast<const float4*>(ep.ln_x + size_t(row) * 256 + col);
+            }
+          }
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * BN + c), v);
+          tmem_ld_wait();
+          {
+            const uint32_t my = stage_buf + lane * (kStageRow * 4);
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              st_shared_v4(my + q * 16, __uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                           __uint_as_float(v[4 * q + 3]));
+          }
+          __syncwarp();
+          const uint32_t lds_base = stage_buf + (rsub * kStageRow + 4 * cg) * 4;
+          const unsigned long long quad0 =
+              ((unsigned long long)(int(row0) + rsub) * 256ull + (unsigned long long)col) >> 2;
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {                 // four rows at a time: their dx_in loads fly together
+            float4 din[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int row = int(row0) + rsub + 4 * (4 * hh + k);
+              din[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (row < M && ep.ln_dx_in != nullptr) din[k] = *reinterpret_cast<const float4*>(ep.ln_dx_in + size_t(row) * 256 + col);
+            }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int i = 4 * hh + k;
+            const int row = int(row0) + rsub + 4 * i;
+            const float4 dy = ld_shared_v4(lds_base + i * (4 * kStageRow * 4));
+            if (row < M) {
+              const float r = rstd[i];
+              float4 o;
+              o.x = dy.x * (r * g4[ci].x) + xv[i].x * s2[i] + s1[i] + din[k].x;
+              o.y = dy.y * (r * g4[ci].y) + xv[i].y * s2[i] + s1[i] + din[k].y;
+              o.z = dy.z * (r * g4[ci].z) + xv[i].z * s2[i] + s1[i] + din[k].z;
+              o.w = dy.w * (r * g4[ci].w) + xv[i].w * s2[i] + s1[i] + din[k].w;
+              if (ep.ln_dx_out != nullptr) *reinterpret_cast<float4*>(ep.ln_dx_out + size_t(row) * 256 + col) = o;
+              if (ep.ln_out != nullptr) {
+                if (has_drop) {
+                  const unsigned long long quad = quad0 + (unsigned long long)i * 256ull;   // row advances by 4: 4 * 256 / 4 quads
+                  const float4 mk = dropout_quad_mult(ep.drop, uint32_t(quad), drop_hikey(ep.drop, quad));
+                  o.x *= mk.x; o.y *= mk.y; o.z *= mk.z; o.w *= mk.w;
+                }
+                st_bf16x4(ep.ln_out + size_t(row) * 256 + col, o.x, o.y, o.z, o.w);
+              }
+            }
+          }
+          }
+          __syncwarp();
+        }
       } else {
         constexpr uint32_t FEAT = kLeanFeat[MODE > 0 ? MODE - 1 : 0];
         // residual / mask operands are fetched one chunk ahead: the first chunk's loads fly while the MMAs of this
@@ -902,6 +1234,13 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     }
     if constexpr (lin_tma_out(MODE)) {
       if (warp == 2 && lane == 0) tma_store_wait_all();   // bulk stores must complete before the CTA's smem goes away
+    }
+    if constexpr (MODE == 9) {
+      named_bar_sync(2, Cfg::kEpiWarps * 32);             // every warp's shared-memory atomics have landed
+      for (int j = threadIdx.x - 64; j < 512; j += Cfg::kEpiWarps * 32) {
+        float* dst = j < 256 ? ep.ln_dgamma : ep.ln_dbeta;
+        if (dst != nullptr) atomicAdd(dst + (j & 255), ln_acc[j]);
+      }
     }
   }
 
@@ -1257,13 +1596,7 @@ extern "C" unsigned long long dsvg_launch_count(void) { return dsvg::g_launches;
 static long long* g_linear_trace = nullptr;
 extern "C" void dsvg_debug_linear_trace(long long* dev_buf_256) { g_linear_trace = dev_buf_256; }
 
-extern "C" int dsvg_linear(const dsvg_bf16* X, size_t x_lo_off, int lda, const dsvg_bf16* W, size_t w_lo_off, int ldb,
-                           int M, int N, int K, const dsvg_epilogue* e, void* stream) {
-  DSVG_CHECK(X && W && e, "dsvg_linear: null pointer");
-  DSVG_CHECK(M > 0 && N > 0 && K > 0, "dsvg_linear: bad shape %d x %d x %d", M, N, K);
-  DSVG_CHECK(lda % 8 == 0 && ldb % 8 == 0, "dsvg_linear: lda/ldb must be multiples of 8 elements (TMA row stride)");
-  DSVG_CHECK((x_lo_off == 0) == (w_lo_off == 0), "dsvg_linear: both operands must have the same number of planes");
-  Epi ep{};
+static int fill_epi(Epi& ep, const dsvg_epilogue* e, int M, int N) {
   ep.acc_scale_dev = e->acc_scale_dev;
   ep.bias = e->bias;
   ep.scale_cols = e->scale_cols;
@@ -1287,7 +1620,6 @@ extern "C" int dsvg_linear(const dsvg_bf16* X, size_t x_lo_off, int lda, const d
   ep.out_act = reinterpret_cast<bf16*>(e->out_act);
   ep.out_lo_off = e->out_lo_off;
   ep.out_act_ld = e->out_act_ld;
-  DSVG_CHECK(ep.out_f32 || ep.out_act, "dsvg_linear: no output requested");
   ep.dbg = g_linear_trace;
   {
     auto al = [](const void* p, size_t a) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % a) == 0; };
@@ -1299,6 +1631,18 @@ extern "C" int dsvg_linear(const dsvg_bf16* X, size_t x_lo_off, int lda, const d
     static const int direct = [] { const char* e = getenv("DSVG_EPI"); return (e && e[0] == 'd') ? 1 : 0; }();  // staged (transposed) epilogue measured 2.2x faster than direct
     ep.vec = v ? (direct ? 2 : 1) : 0;
   }
+  return 0;
+}
+
+extern "C" int dsvg_linear(const dsvg_bf16* X, size_t x_lo_off, int lda, const dsvg_bf16* W, size_t w_lo_off, int ldb,
+                           int M, int N, int K, const dsvg_epilogue* e, void* stream) {
+  DSVG_CHECK(X && W && e, "dsvg_linear: null pointer");
+  DSVG_CHECK(M > 0 && N > 0 && K > 0, "dsvg_linear: bad shape %d x %d x %d", M, N, K);
+  DSVG_CHECK(lda % 8 == 0 && ldb % 8 == 0, "dsvg_linear: lda/ldb must be multiples of 8 elements (TMA row stride)");
+  DSVG_CHECK((x_lo_off == 0) == (w_lo_off == 0), "dsvg_linear: both operands must have the same number of planes");
+  Epi ep{};
+  if (fill_epi(ep, e, M, N)) return 1;
+  DSVG_CHECK(ep.out_f32 || ep.out_act, "dsvg_linear: no output requested");
   const bool split = x_lo_off != 0;
   static const bool force128 = [] { const char* e = getenv("DSVG_BN128"); return e && e[0] == '1'; }();
   // 256-wide tiles for the big path-level GEMMs; the group-level ones (M = N_icons * 8 rows, a few dozen tiles) run the
@@ -1321,6 +1665,67 @@ extern "C" int dsvg_linear(const dsvg_bf16* X, size_t x_lo_off, int lda, const d
   ep.mode = pick_mode(ep, split, N);
   if (split) return launch_linear_mode<128, 2, 0>(a, alo, b, blo, M, N, K, ep, st);
   return wide ? launch_linear_fast<256>(a, b, M, N, K, ep, st) : launch_linear_fast<128>(a, b, M, N, K, ep, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// GEMM + LayerNorm in one kernel (fast mode, d_model = 256 rows owned by one CTA tile, path-level row counts)
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int dsvg_linear_ln_fusable(int M, int N, int n_planes) {
+  static const bool off = [] { const char* e = getenv("DSVG_LN_FUSE"); return e && e[0] == '0'; }();
+  return (!off && n_planes == 1 && N == 256 && M > 16384) ? 1 : 0;
+}
+
+static int ln_common_checks(const dsvg_bf16* X, size_t x_lo_off, int lda, const dsvg_bf16* W, size_t w_lo_off, int ldb, int M,
+                            int N, int K) {
+  DSVG_CHECK(X && W, "dsvg_linear_ln: null pointer");
+  DSVG_CHECK(M > 0 && K > 0, "dsvg_linear_ln: bad shape");
+  DSVG_CHECK(lda % 8 == 0 && ldb % 8 == 0, "dsvg_linear_ln: lda/ldb must be multiples of 8 elements");
+  DSVG_CHECK(x_lo_off == 0 && w_lo_off == 0 && dsvg_linear_ln_fusable(M, N, 1),
+             "dsvg_linear_ln: shape / mode not fusable (ask dsvg_linear_ln_fusable first)");
+  return 0;
+}
+
+extern "C" int dsvg_linear_ln_fwd(const dsvg_bf16* X, size_t x_lo_off, int lda, const dsvg_bf16* W, size_t w_lo_off, int ldb,
+                                  int M, int N, int K, const dsvg_epilogue* e, const float* gamma, const float* beta,
+                                  dsvg_bf16* y, float* mean, float* rstd, void* stream) {
+  if (ln_common_checks(X, x_lo_off, lda, W, w_lo_off, ldb, M, N, K)) return 1;
+  DSVG_CHECK(e && gamma && beta && y && mean && rstd, "dsvg_linear_ln_fwd: null pointer");
+  Epi ep{};
+  if (fill_epi(ep, e, M, N)) return 1;
+  DSVG_CHECK(ep.out_f32 && !ep.out_act && !ep.mask && !ep.relu && ep.scale_cols == 0 && !ep.acc_scale_dev && ep.vec == 1,
+             "dsvg_linear_ln_fwd: the epilogue must be the residual-stream form (bias, dropout, row vector, residual -> fp32)");
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  DSVG_CHECK(al16(gamma) && al16(beta) && al16(y), "dsvg_linear_ln_fwd: gamma / beta / y must be 16-byte aligned");
+  ep.ln_gamma = gamma; ep.ln_beta = beta; ep.ln_out = reinterpret_cast<bf16*>(y); ep.ln_mean = mean; ep.ln_rstd = rstd;
+  ep.mode = 8;
+  CUtensorMap a, b;
+  if (make_map(&a, reinterpret_cast<const bf16*>(X), K, M, lda, 64, 128)) return 1;
+  if (make_map(&b, reinterpret_cast<const bf16*>(W), K, N, ldb, 64, 256)) return 1;
+  return launch_linear_mode<256, 1, 8>(a, a, b, b, M, N, K, ep, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int dsvg_linear_ln_bwd(const dsvg_bf16* dY, size_t dy_lo_off, int lda, const dsvg_bf16* W, size_t w_lo_off, int ldb,
+                                  int M, int N, int K, const float* x, const float* mean, const float* rstd,
+                                  const float* gamma, const float* dx_in, float* dx_out, dsvg_bf16* dact, float drop_p,
+                                  uint32_t drop_site, uint64_t seed, float* dgamma, float* dbeta, void* stream) {
+  if (ln_common_checks(dY, dy_lo_off, lda, W, w_lo_off, ldb, M, N, K)) return 1;
+  DSVG_CHECK(x && mean && rstd && gamma && (dx_out || dact), "dsvg_linear_ln_bwd: null pointer");
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  DSVG_CHECK(al16(x) && al16(gamma) && al16(dx_in) && al16(dx_out) && al16(dact),
+             "dsvg_linear_ln_bwd: x / gamma / dx_in / dx_out / dact must be 16-byte aligned");
+  Epi ep{};
+  ep.rows_per_group = 1;
+  ep.vec = 1;
+  ep.drop = make_dropout(drop_p, drop_site, seed);
+  ep.ln_x = x; ep.ln_mean = const_cast<float*>(mean); ep.ln_rstd = const_cast<float*>(rstd); ep.ln_gamma = gamma;
+  ep.ln_dx_in = dx_in; ep.ln_dx_out = dx_out; ep.ln_out = reinterpret_cast<bf16*>(dact);
+  ep.ln_dgamma = dgamma; ep.ln_dbeta = dbeta;
+  ep.mode = 9;
+  ep.dbg = nullptr;
+  CUtensorMap a, b;
+  if (make_map(&a, reinterpret_cast<const bf16*>(dY), K, M, lda, 64, 128)) return 1;
+  if (make_map(&b, reinterpret_cast<const bf16*>(W), K, N, ldb, 64, 256)) return 1;
+  return launch_linear_mode<256, 1, 9>(a, a, b, b, M, N, K, ep, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int dsvg_outer(const dsvg_bf16* A, size_t a_lo_off, int lda, const dsvg_bf16* B, size_t b_lo_off, int ldb,

@@ -424,16 +424,23 @@ class SVGTransformer(nn.Module):
         # bit 31 of the site: `seed` is a device pointer (include/dsvg_b200.h, DSVG_SEED_IS_DEVICE_PTR)
         return (self.cfg.dropout if p is None else p, self._site(tag) | 0x80000000, sv.seed_ptr)
 
-    def _layer_fwd(self, sv, pre, x, M, L, nseq, key_valid, rowvec, rpg):
+    def _layer_fwd(self, sv, pre, x, M, L, nseq, key_valid, rowvec, rpg, a_pre=None, next_ln=None):
+        """One pre-LN block.  a_pre = (LN1(x) Act, mean, rstd) when the previous GEMM already produced it in its epilogue;
+        next_ln = (gamma, beta) of the LayerNorm that consumes this block's output (next layer's norm1 or the stack's final
+        norm): when the GEMM tile owns whole rows (ops.ln_fusable) it is computed in the FFN2 epilogue and returned."""
         cfg = self.cfg
         d, ff, H = cfg.d_model, cfg.dim_feedforward, cfg.n_heads
         hd = d // H
         dev, pl = x.device, self.planes
         P = lambda n: self._param(pre + "." + n)
+        fuse = ops.ln_fusable(M, d, pl)
         s = {}
-        a = Act(M, d, pl, dev)
-        s["mean1"], s["rstd1"] = torch.empty(M, device=dev), torch.empty(M, device=dev)
-        ops.ln_fwd(x, P("norm1.weight"), P("norm1.bias"), a, s["mean1"], s["rstd1"], M, d)
+        if a_pre is not None:
+            a, s["mean1"], s["rstd1"] = a_pre
+        else:
+            a = Act(M, d, pl, dev)
+            s["mean1"], s["rstd1"] = torch.empty(M, device=dev), torch.empty(M, device=dev)
+            ops.ln_fwd(x, P("norm1.weight"), P("norm1.bias"), a, s["mean1"], s["rstd1"], M, d)
         qkv = Act(M, 3 * d, pl, dev)
         w_in, _ = self._pack(pre + ".self_attn.in_proj_weight")
         ops.linear(a, w_in, M, 3 * d, d, bias=P("self_attn.in_proj_bias"), scale_cols=d, scale=float(hd) ** -0.5,
@@ -442,21 +449,26 @@ class SVGTransformer(nn.Module):
         ops.attn_fwd(qkv, key_valid, o, nseq, L, H, hd, self._drop(sv, pre + ".attn"))
         x1 = torch.empty(M, d, device=dev)
         w_o, _ = self._pack(pre + ".self_attn.out_proj.weight")
-        ops.linear(o, w_o, M, d, d, bias=P("self_attn.out_proj.bias"), drop=self._drop(sv, pre + ".drop1"),
-                   rowvec=rowvec, rows_per_group=rpg, residual=x, out_f32=x1)
         b = Act(M, d, pl, dev)
         s["mean2"], s["rstd2"] = torch.empty(M, device=dev), torch.empty(M, device=dev)
-        ops.ln_fwd(x1, P("norm2.weight"), P("norm2.bias"), b, s["mean2"], s["rstd2"], M, d)
+        ops.linear(o, w_o, M, d, d, bias=P("self_attn.out_proj.bias"), drop=self._drop(sv, pre + ".drop1"),
+                   rowvec=rowvec, rows_per_group=rpg, residual=x, out_f32=x1,
+                   ln=(P("norm2.weight"), P("norm2.bias"), b, s["mean2"], s["rstd2"]) if fuse else None)
+        if not fuse:
+            ops.ln_fwd(x1, P("norm2.weight"), P("norm2.bias"), b, s["mean2"], s["rstd2"], M, d)
         h = Act(M, ff, pl, dev)
         w1, _ = self._pack(pre + ".linear1.weight")
         ops.linear(b, w1, M, ff, d, bias=P("linear1.bias"), relu=True, drop=self._drop(sv, pre + ".dropff"), out_act=h)
         x2 = torch.empty(M, d, device=dev)
         w2, _ = self._pack(pre + ".linear2.weight")
+        nxt = None
+        if fuse and next_ln is not None:
+            nxt = (Act(M, d, pl, dev), torch.empty(M, device=dev), torch.empty(M, device=dev))
         ops.linear(h, w2, M, d, ff, bias=P("linear2.bias"), drop=self._drop(sv, pre + ".drop2"), residual=x1,
-                   out_f32=x2)
+                   out_f32=x2, ln=(next_ln[0], next_ln[1]) + nxt if nxt is not None else None)
         s.update(x=x, a=a, qkv=qkv, o=o, x1=x1, b=b, h=h)
         sv.layers[pre] = s
-        return x2
+        return x2, nxt
 
     def _globals_fwd(self, sv, pre, zmem, n_groups, lab, lab_rpg):
         """rowvec of a layer: dropout(linear_global(zmem)) [+ dropout(linear_global2(label))]
@@ -480,14 +492,22 @@ class SVGTransformer(nn.Module):
         return g
 
     def _stack_fwd(self, sv, pre, n_layers, x, M, L, nseq, key_valid, zmem=None, lab=None, lab_rows_per_group=1,
-                   lab_rpg=1):
-        """L = sequence length; rows of one rowvec group = L (zmem per sequence) or lab_rows_per_group (label only)."""
+                   lab_rpg=1, final_ln=False):
+        """L = sequence length; rows of one rowvec group = L (zmem per sequence) or lab_rows_per_group (label only).
+        Returns (x, final) -- final = (LN_f(x) Act, mean, rstd) when final_ln was requested AND the last FFN2 epilogue
+        could produce it (otherwise None: the caller runs the stand-alone LayerNorm kernel)."""
+        nxt = None
         for i in range(n_layers):
             lp = "%s.layers.%d" % (pre, i)
             rv = self._globals_fwd(sv, lp, zmem, nseq, lab, lab_rpg) if (zmem is not None or lab is not None) else None
             rpg = L if zmem is not None else lab_rows_per_group
-            x = self._layer_fwd(sv, lp, x, M, L, nseq, key_valid, rv, rpg)
-        return x
+            if i + 1 < n_layers:
+                nl = "%s.layers.%d" % (pre, i + 1)
+                next_ln = (self._param(nl + ".norm1.weight"), self._param(nl + ".norm1.bias"))
+            else:
+                next_ln = (self._param(pre + ".norm.weight"), self._param(pre + ".norm.bias")) if final_ln else None
+            x, nxt = self._layer_fwd(sv, lp, x, M, L, nseq, key_valid, rv, rpg, a_pre=nxt, next_ln=next_ln)
+        return x, nxt
 
     def _forward_impl(self, inp, seed_dev=None):
         cfg = self.cfg
@@ -547,8 +567,8 @@ class SVGTransformer(nn.Module):
                 ops.gather_rows(P("encoder.label_embedding.label_embedding.weight"), label, N, cfg.dim_label, lab_e)
             sv.lab_e = lab_e
             # ---- E1 (model.py:135-137) ----
-            x = self._stack_fwd(sv, "encoder.encoder", cfg.n_layers, x, M1, L, nseq, sv.key_valid, lab=lab_e,
-                                lab_rows_per_group=G * L)
+            x, _ = self._stack_fwd(sv, "encoder.encoder", cfg.n_layers, x, M1, L, nseq, sv.key_valid, lab=lab_e,
+                                   lab_rows_per_group=G * L)
             sv.e1_x = x
             zp = torch.empty(nseq, d, device=dev)
             sv.e1_mean, sv.e1_rstd = torch.empty(M1, device=dev), torch.empty(M1, device=dev)
@@ -560,8 +580,8 @@ class SVGTransformer(nn.Module):
                 x = torch.empty(nseq, d, device=dev)
                 ops.rows_embed_fwd(zp, P("encoder.hierarchical_PE.pos_embed.weight"), x, nseq, G, d,
                                    self._drop(sv, "enc.pe2", 0.1))
-                x = self._stack_fwd(sv, "encoder.hierarchical_encoder", cfg.n_layers, x, nseq, G, N, sv.visible,
-                                    lab=lab_e, lab_rows_per_group=G)
+                x, _ = self._stack_fwd(sv, "encoder.hierarchical_encoder", cfg.n_layers, x, nseq, G, N, sv.visible,
+                                       lab=lab_e, lab_rows_per_group=G)
                 sv.e2_x = x
                 z = torch.empty(N, d, device=dev)
                 sv.e2_mean, sv.e2_rstd = torch.empty(nseq, device=dev), torch.empty(nseq, device=dev)
@@ -626,13 +646,16 @@ class SVGTransformer(nn.Module):
             x = torch.empty(nq, d, device=dev)
             ops.rows_embed_fwd(None, P("decoder.hierarchical_embedding.PE.pos_embed.weight"), x, nq, Gp, d,
                                self._drop(sv, "dec.pe2", 0.1))
-            x = self._stack_fwd(sv, "decoder.hierarchical_decoder", cfg.n_layers_decode, x, nq, Gp, N, None,
-                                zmem=z_act, lab=lab_d, lab_rpg=1)
+            x, fin = self._stack_fwd(sv, "decoder.hierarchical_decoder", cfg.n_layers_decode, x, nq, Gp, N, None,
+                                     zmem=z_act, lab=lab_d, lab_rpg=1, final_ln=True)
             sv.d2_x = x
-            y = Act(nq, d, pl, dev)
-            sv.d2_mean, sv.d2_rstd = torch.empty(nq, device=dev), torch.empty(nq, device=dev)
-            ops.ln_fwd(x, P("decoder.hierarchical_decoder.norm.weight"), P("decoder.hierarchical_decoder.norm.bias"), y,
-                       sv.d2_mean, sv.d2_rstd, nq, d)
+            if fin is not None:
+                y, sv.d2_mean, sv.d2_rstd = fin
+            else:
+                y = Act(nq, d, pl, dev)
+                sv.d2_mean, sv.d2_rstd = torch.empty(nq, device=dev), torch.empty(nq, device=dev)
+                ops.ln_fwd(x, P("decoder.hierarchical_decoder.norm.weight"), P("decoder.hierarchical_decoder.norm.bias"),
+                           y, sv.d2_mean, sv.d2_rstd, nq, d)
             sv.d2_y = y
             vis_logits = torch.empty(nq, 2, device=dev)
             w, _ = self._pack("decoder.hierarchical_fcn.visibility_fcn.weight")
@@ -652,12 +675,15 @@ class SVGTransformer(nn.Module):
         sv.nseq_d, sv.Ld, sv.Md = nseq_d, Ld, Md
         x = torch.empty(Md, d, device=dev)
         ops.rows_embed_fwd(None, P("decoder.embedding.PE.pos_embed.weight"), x, Md, Ld, d, self._drop(sv, "dec.pe", 0.1))
-        x = self._stack_fwd(sv, "decoder.decoder", cfg.n_layers_decode, x, Md, Ld, nseq_d, None, zmem=zmem, lab=lab_d,
-                            lab_rpg=lab_rpg)
+        x, fin = self._stack_fwd(sv, "decoder.decoder", cfg.n_layers_decode, x, Md, Ld, nseq_d, None, zmem=zmem, lab=lab_d,
+                                 lab_rpg=lab_rpg, final_ln=True)
         sv.d1_x = x
-        y = Act(Md, d, pl, dev)
-        sv.d1_mean, sv.d1_rstd = torch.empty(Md, device=dev), torch.empty(Md, device=dev)
-        ops.ln_fwd(x, P("decoder.decoder.norm.weight"), P("decoder.decoder.norm.bias"), y, sv.d1_mean, sv.d1_rstd, Md, d)
+        if fin is not None:
+            y, sv.d1_mean, sv.d1_rstd = fin
+        else:
+            y = Act(Md, d, pl, dev)
+            sv.d1_mean, sv.d1_rstd = torch.empty(Md, device=dev), torch.empty(Md, device=dev)
+            ops.ln_fwd(x, P("decoder.decoder.norm.weight"), P("decoder.decoder.norm.bias"), y, sv.d1_mean, sv.d1_rstd, Md, d)
         sv.d1_y = y
         nc, na_out = cfg.n_commands, cfg.n_args * self.args_dim
         cmd_logits = torch.empty(Md, nc, device=dev)
@@ -693,13 +719,18 @@ class SVGTransformer(nn.Module):
         _, w2t = self._pack(pre + ".linear2.weight")
         ops.linear(dx2_act, w2t, M, ff, d, mask=s["h"], mask_scale=1.0 / (1.0 - pff[0]) if pff[0] > 0 else 1.0, out_act=dh)
         ops.outer(dh, s["b"], M, ff, d, G("linear1.weight"), colsum=G("linear1.bias"))
-        db = Act(M, d, pl, dev)
+        fuse = ops.ln_fusable(M, d, pl)
         _, w1t = self._pack(pre + ".linear1.weight")
-        ops.linear(dh, w1t, M, d, ff, out_act=db)
         dx1 = torch.empty(M, d, device=dev)
         dt = Act(M, d, pl, dev)
-        ops.ln_bwd(s["x1"], s["mean2"], s["rstd2"], P("norm2.weight"), M, d, dy=db, dx_in=dx2, dx_out=dx1, dact=dt,
-                   drop=self._drop(sv, pre + ".drop1"), dgamma=G("norm2.weight"), dbeta=G("norm2.bias"))
+        if fuse:    # FFN1 input gradient + LayerNorm-2 backward in one kernel: the bf16 gradient `db` never exists in HBM
+            ops.linear_ln_bwd(dh, w1t, M, d, ff, s["x1"], s["mean2"], s["rstd2"], P("norm2.weight"), dx_in=dx2, dx_out=dx1,
+                              dact=dt, drop=self._drop(sv, pre + ".drop1"), dgamma=G("norm2.weight"), dbeta=G("norm2.bias"))
+        else:
+            db = Act(M, d, pl, dev)
+            ops.linear(dh, w1t, M, d, ff, out_act=db)
+            ops.ln_bwd(s["x1"], s["mean2"], s["rstd2"], P("norm2.weight"), M, d, dy=db, dx_in=dx2, dx_out=dx1, dact=dt,
+                       drop=self._drop(sv, pre + ".drop1"), dgamma=G("norm2.weight"), dbeta=G("norm2.bias"))
         # ---- attention ----
         ops.outer(dt, s["o"], M, d, d, G("self_attn.out_proj.weight"), colsum=G("self_attn.out_proj.bias"))
         do = Act(M, d, pl, dev)
@@ -708,13 +739,17 @@ class SVGTransformer(nn.Module):
         dqkv = Act(M, 3 * d, pl, dev)
         ops.attn_bwd(s["qkv"], key_valid, do, dqkv, nseq, L, H, hd, float(hd) ** -0.5, self._drop(sv, pre + ".attn"))
         ops.outer(dqkv, s["a"], M, 3 * d, d, G("self_attn.in_proj_weight"), colsum=G("self_attn.in_proj_bias"))
-        da = Act(M, d, pl, dev)
         _, wit = self._pack(pre + ".self_attn.in_proj_weight")
-        ops.linear(dqkv, wit, M, d, 3 * d, out_act=da)
         dx0 = torch.empty(M, d, device=dev)
         dx0_act = Act(M, d, pl, dev) if want_dact else None
-        ops.ln_bwd(s["x"], s["mean1"], s["rstd1"], P("norm1.weight"), M, d, dy=da, dx_in=dx1, dx_out=dx0, dact=dx0_act,
-                   drop=prev_drop, dgamma=G("norm1.weight"), dbeta=G("norm1.bias"))
+        if fuse:
+            ops.linear_ln_bwd(dqkv, wit, M, d, 3 * d, s["x"], s["mean1"], s["rstd1"], P("norm1.weight"), dx_in=dx1,
+                              dx_out=dx0, dact=dx0_act, drop=prev_drop, dgamma=G("norm1.weight"), dbeta=G("norm1.bias"))
+        else:
+            da = Act(M, d, pl, dev)
+            ops.linear(dqkv, wit, M, d, 3 * d, out_act=da)
+            ops.ln_bwd(s["x"], s["mean1"], s["rstd1"], P("norm1.weight"), M, d, dy=da, dx_in=dx1, dx_out=dx0, dact=dx0_act,
+                       drop=prev_drop, dgamma=G("norm1.weight"), dbeta=G("norm1.bias"))
         return dx0, dx0_act, dx1
 
     def _globals_bwd(self, sv, gd, pre, dx1, n_groups, L, zmem, dzmem, lab, dlab, lab_rows_per_group, lab_rpg):

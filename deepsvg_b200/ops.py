@@ -77,9 +77,16 @@ def act_from_float(x, planes, ld=None):
     return a
 
 
+def ln_fusable(M, N, planes):
+    """True when the GEMM's CTA tile owns whole LayerNorm rows, so that linear_ln_fwd / linear_ln_bwd apply."""
+    return bool(_lib.load().dsvg_linear_ln_fusable(M, N, planes))
+
+
 def linear(X, W, M, N, K, *, bias=None, scale_cols=0, scale=1.0, relu=False, drop=(0.0, 0, 0), rowvec=None,
-           rows_per_group=1, mask=None, mask_scale=1.0, residual=None, out_f32=None, out_act=None, acc_scale=None):
-    """out = epilogue(X[M,K] . W[N,K]^T); X, W are Act."""
+           rows_per_group=1, mask=None, mask_scale=1.0, residual=None, out_f32=None, out_act=None, acc_scale=None,
+           ln=None):
+    """out = epilogue(X[M,K] . W[N,K]^T); X, W are Act.
+    ln = (gamma, beta, y Act, mean, rstd): additionally y = LayerNorm(out_f32) in the same kernel (needs ln_fusable)."""
     ep = Epilogue()
     ep.acc_scale_dev = _p(acc_scale)
     ep.bias = _p(bias)
@@ -95,9 +102,28 @@ def linear(X, W, M, N, K, *, bias=None, scale_cols=0, scale=1.0, relu=False, dro
         ep.out_f32, ep.out_f32_ld = out_f32.data_ptr(), out_f32.stride(0)
     if out_act is not None:
         ep.out_act, ep.out_lo_off, ep.out_act_ld = out_act.ptr, out_act.lo, out_act.ld
+    if ln is not None:
+        gamma, beta, y, mean, rstd = ln
+        with _Prof("linear", 2.0 * M * N * K, (M, N, K)):
+            rc = _lib.load().dsvg_linear_ln_fwd(X.ptr, X.lo, X.ld, W.ptr, W.lo, W.ld, M, N, K, C.byref(ep), gamma.data_ptr(),
+                                                beta.data_ptr(), y.ptr, mean.data_ptr(), rstd.data_ptr(), _stream())
+        _lib.check(rc, "dsvg_linear_ln_fwd")
+        return
     with _Prof("linear", 2.0 * M * N * K, (M, N, K)):
         rc = _lib.load().dsvg_linear(X.ptr, X.lo, X.ld, W.ptr, W.lo, W.ld, M, N, K, C.byref(ep), _stream())
     _lib.check(rc, "dsvg_linear")
+
+
+def linear_ln_bwd(dY, W, M, N, K, x, mean, rstd, gamma, *, dx_in=None, dx_out=None, dact=None, drop=(0.0, 0, 0),
+                  dgamma=None, dbeta=None):
+    """dgrad GEMM dY[M,K] . W[N,K]^T whose result is the gradient at a LayerNorm output, fused with that LayerNorm's
+    backward (see include/dsvg_b200.h); same outputs as linear(..., out_act=dy) followed by ln_bwd(dy=dy, ...)."""
+    with _Prof("linear", 2.0 * M * N * K, (M, N, K)):
+        rc = _lib.load().dsvg_linear_ln_bwd(dY.ptr, dY.lo, dY.ld, W.ptr, W.lo, W.ld, M, N, K, x.data_ptr(), mean.data_ptr(),
+                                            rstd.data_ptr(), gamma.data_ptr(), _p(dx_in), _p(dx_out),
+                                            dact.ptr if dact is not None else 0, drop[0], drop[1], drop[2], _p(dgamma),
+                                            _p(dbeta), _stream())
+    _lib.check(rc, "dsvg_linear_ln_bwd")
 
 
 def outer(A, B, M, P, Q, Cout, *, alpha=1.0, alpha_dev=None, colsum=None):

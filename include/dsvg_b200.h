@@ -83,6 +83,27 @@ int dsvg_linear(const dsvg_bf16* X, size_t x_lo_off, int lda, const dsvg_bf16* W
 int dsvg_outer(const dsvg_bf16* A, size_t a_lo_off, int lda, const dsvg_bf16* B, size_t b_lo_off, int ldb, int M,
                int P, int Q, float alpha, const float* alpha_dev, float* C, int ldc, float* colsum_out, void* stream);
 
+/* GEMM + LayerNorm in one kernel (fast mode).  When the CTA tile of dsvg_linear owns whole rows (N = d_model = 256,
+ * path-level row counts, single-plane operands: ask dsvg_linear_ln_fusable) the LayerNorm that follows a residual-stream
+ * linear, and the LayerNorm backward that follows the input-gradient GEMM of the layer's QKV / FFN1 linear, run in that
+ * GEMM's epilogue: the fp32 residual stream is not re-read by a separate kernel and the bf16 dgrad never goes to HBM.
+ *   forward  (improved_transformer.py:43-44 -> :51, :52-53 -> next layer's :43 / transformer.py:185-186):
+ *       x1 = epilogue `e` (bias, dropout, row vector, residual -> e->out_f32 [M,256], row stride e->out_f32_ld)
+ *       y  = bf16(LayerNorm(x1) * gamma + beta) [M,256];  mean[M], rstd[M] saved for the backward
+ *   backward (autograd of the same lines):  dy = dY[M,K] . W[256,K]^T  (stays on chip)
+ *       dx_out = rstd * (dy*gamma - mean_j(dy*gamma) - xhat * mean_j(dy*gamma*xhat)) + dx_in      (fp32 [M,256])
+ *       dact   = bf16(dropout_mask(drop_p, site, seed)[row*256+col] * dx_out)                      (optional)
+ *       dgamma += sum_rows dy * xhat ;  dbeta += sum_rows dy                                        (optional)
+ * Results equal dsvg_linear followed by dsvg_ln_fwd / dsvg_ln_bwd (tests/test_kernels_gpu.py). */
+int dsvg_linear_ln_fusable(int M, int N, int n_planes);
+int dsvg_linear_ln_fwd(const dsvg_bf16* X, size_t x_lo_off, int lda, const dsvg_bf16* W, size_t w_lo_off, int ldb, int M,
+                       int N, int K, const dsvg_epilogue* e, const float* gamma, const float* beta, dsvg_bf16* y,
+                       float* mean, float* rstd, void* stream);
+int dsvg_linear_ln_bwd(const dsvg_bf16* dY, size_t dy_lo_off, int lda, const dsvg_bf16* W, size_t w_lo_off, int ldb, int M,
+                       int N, int K, const float* x, const float* mean, const float* rstd, const float* gamma,
+                       const float* dx_in, float* dx_out, dsvg_bf16* dact, float drop_p, uint32_t drop_site, uint64_t seed,
+                       float* dgamma, float* dbeta, void* stream);
+
 /* ---- sequence bookkeeping (model/utils.py:7-66) ------------------------------------------------------ */
 /* From commands[nseq, L] (ids stored as float): first_eos[nseq], visible[nseq] (#EOS < L-1), key_valid[nseq*L]
  * (1 before the first EOS), grp[nseq*L] (# of "m" so far), counts[2] += {loss_cmd positions, loss_args slots}.

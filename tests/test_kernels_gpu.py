@@ -179,6 +179,80 @@ def test_layernorm_fwd_bwd(D):
     assert _rel(dg, gr.grad) < 2e-5 and _rel(db, br.grad) < 2e-5
 
 
+@pytest.mark.parametrize("M,K,rowvec,drop_p", [(16500, 256, False, 0.0), (16500, 512, True, 0.1), (33000, 256, True, 0.1),
+                                               (20000, 512, False, 0.2)])
+def test_linear_layernorm_fused_forward(M, K, rowvec, drop_p):
+    """dsvg_linear_ln_fwd == dsvg_linear (residual-stream epilogue) followed by dsvg_ln_fwd: same fp32 residual stream bit
+    for bit (same arithmetic, same dropout draws), LayerNorm output and statistics to rounding; and against plain fp32
+    torch when dropout is off."""
+    ops = _ops()
+    N = 256
+    assert ops.ln_fusable(M, N, 1) and not ops.ln_fusable(M, N, 2) and not ops.ln_fusable(4096, N, 1)
+    X = ops.act_from_float(_rand(M, K, seed=1, scale=0.5), 1)
+    W = ops.act_from_float(_rand(N, K, seed=2, scale=0.1), 1)
+    bias, res = _rand(N, seed=3), _rand(M, N, seed=4, scale=2.0) + 1.5      # a non-zero row mean (variance by E[x^2]-m^2)
+    g, b = 1 + 0.1 * _rand(N, seed=5), 0.1 * _rand(N, seed=6)
+    L = 31
+    rv = _rand((M + L - 1) // L, N, seed=7) if rowvec else None
+    drop = (drop_p, 5, 1234) if drop_p > 0 else (0.0, 0, 0)
+    kw = dict(bias=bias, drop=drop, rowvec=rv, rows_per_group=L if rowvec else 1, residual=res)
+    x_a, x_b = torch.empty(M, N, device=DEV), torch.empty(M, N, device=DEV)
+    y_a, y_b = ops.Act(M, N, 1, DEV), ops.Act(M, N, 1, DEV)
+    m_a, r_a, m_b, r_b = (torch.empty(M, device=DEV) for _ in range(4))
+    ops.linear(X, W, M, N, K, out_f32=x_a, **kw)
+    ops.ln_fwd(x_a, g, b, y_a, m_a, r_a, M, N)
+    ops.linear(X, W, M, N, K, out_f32=x_b, ln=(g, b, y_b, m_b, r_b), **kw)
+    assert (x_a - x_b).abs().max().item() <= 2e-6 * x_a.abs().max().item()      # same arithmetic up to FMA contraction
+    assert _rel(m_b, m_a) < 1e-5 and _rel(r_b, r_a) < 1e-4
+    # the two outputs are bf16 roundings of values that agree to ~1e-6: at most one bf16 ulp apart
+    assert ((y_a.float() - y_b.float()).abs() <= 2.0 ** -7 * y_a.float().abs() + 1e-6).all()
+    assert (y_a.t != y_b.t).float().mean().item() < 0.02
+    if drop_p == 0:
+        ref = X.float() @ W.float().t() + bias + res
+        if rowvec:
+            ref = ref + rv[torch.arange(M, device=DEV) // L]
+        assert _rel(x_b, ref) < 1e-5
+        assert _rel(y_b.float(), F.layer_norm(ref, (N,), g, b, 1e-5)) < 1e-2
+
+
+@pytest.mark.parametrize("M,K,drop_p,with_in,with_act", [(16500, 512, 0.0, True, True), (16500, 768, 0.1, True, True),
+                                                         (33000, 512, 0.1, False, True), (20000, 768, 0.0, True, False)])
+def test_linear_layernorm_fused_backward(M, K, drop_p, with_in, with_act):
+    """dsvg_linear_ln_bwd: dy = dY . W^T stays on chip (fp32), LayerNorm backward in the epilogue -- against fp32 torch
+    autograd of LayerNorm fed with the fp32 product, and the dropout zero pattern against the stand-alone ln_bwd kernel."""
+    ops = _ops()
+    N = 256
+    dY = ops.act_from_float(_rand(M, K, seed=1, scale=0.5), 1)
+    Wt = ops.act_from_float(_rand(N, K, seed=2, scale=0.1), 1)
+    x = _rand(M, N, seed=3, scale=1.5) + 0.7
+    g = 1 + 0.1 * _rand(N, seed=5)
+    b = torch.zeros(N, device=DEV)
+    mean, rstd = torch.empty(M, device=DEV), torch.empty(M, device=DEV)
+    ops.ln_fwd(x, g, b, ops.Act(M, N, 1, DEV), mean, rstd, M, N)
+    dx_in = _rand(M, N, seed=6) if with_in else None
+    drop = (drop_p, 9, 77) if drop_p > 0 else (0.0, 0, 0)
+    dx = torch.empty(M, N, device=DEV)
+    dact = ops.Act(M, N, 1, DEV) if with_act else None
+    dg, db = torch.zeros(N, device=DEV), torch.zeros(N, device=DEV)
+    ops.linear_ln_bwd(dY, Wt, M, N, K, x, mean, rstd, g, dx_in=dx_in, dx_out=dx, dact=dact, drop=drop, dgamma=dg, dbeta=db)
+    dy = dY.float() @ Wt.float().t()
+    xr, gr, br = x.clone().requires_grad_(True), g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    F.layer_norm(xr, (N,), gr, br, 1e-5).backward(dy)
+    want = xr.grad + (dx_in if with_in else 0)
+    assert _rel(dx, want) < 5e-5
+    assert _rel(dg, gr.grad) < 1e-4 and _rel(db, br.grad) < 1e-4
+    if with_act:
+        dact2, dx2 = ops.Act(M, N, 1, DEV), torch.empty(M, N, device=DEV)
+        ops.ln_bwd(x, mean, rstd, g, M, N, dy=ops.act_from_float(dy, 1), dx_in=dx_in, dx_out=dx2, dact=dact2, drop=drop)
+        if drop_p > 0:
+            z1, z2 = dact.float() == 0, dact2.float() == 0
+            assert abs(z1.float().mean().item() - drop_p) < 0.01 and (z1 != z2).float().mean().item() < 1e-4
+            keep = ~z1
+            assert _rel(dact.float()[keep], (want / (1 - drop_p))[keep]) < 1e-2
+        else:
+            assert _rel(dact.float(), want) < 1e-2
+
+
 def test_layernorm_pool_fwd_bwd():
     ops = _ops()
     nseq, L, D = 96, 31, 256

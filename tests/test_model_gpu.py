@@ -105,7 +105,7 @@ def test_parity_mode_matches_reference_golden(name):
     label = torch.from_numpy(fx["label"]) if "label" in fx else None
     eps = torch.from_numpy(fx["eps"]).float() if "eps" in fx else None
     out, ls, grads = _run(model, loss_fn, cmd, arg, label, eps)
-    idx = lambda t, n: t.reshape(-1)[torch.linspace(0, t.numel() - 1, n).long()]
+    idx = lambda t, n: t.reshape(-1)[torch.linspace(0, t.numel() - 1, n).long().clamp_(max=t.numel() - 1)]
     for k in ("command_logits", "args_logits", "visibility_logits", "mu", "logsigma"):
         if "O_" + k not in fx:
             continue
@@ -130,7 +130,7 @@ def test_fast_mode_on_baseline_configs_4_and_5(name):
     label = torch.from_numpy(fx["label"]) if "label" in fx else None
     eps = torch.from_numpy(fx["eps"]).float() if "eps" in fx else None
     out, ls, grads = _run(model, loss_fn, cmd, arg, label, eps)
-    idx = lambda t, n: t.reshape(-1)[torch.linspace(0, t.numel() - 1, n).long()]
+    idx = lambda t, n: t.reshape(-1)[torch.linspace(0, t.numel() - 1, n).long().clamp_(max=t.numel() - 1)]
     got = idx(out["args_logits"].detach().cpu(), 4096)
     assert (got - torch.from_numpy(fx["O_args_logits"].reshape(-1)).float()).abs().max().item() < 0.08
     assert abs(ls["loss"].item() - float(fx["L_loss"])) < 2e-2 * float(fx["L_loss"])
@@ -252,7 +252,7 @@ def test_parity_mode_on_edge_inputs_matches_reference_golden():
     model, loss_fn, _ = _build(cfg, "bf16x3", seed=int(fx["seed_params"]))
     cmd, arg = torch.from_numpy(fx["commands"]), torch.from_numpy(fx["args"])
     out, ls, grads = _run(model, loss_fn, cmd, arg)
-    idx = lambda t, n: t.reshape(-1)[torch.linspace(0, t.numel() - 1, n).long()]
+    idx = lambda t, n: t.reshape(-1)[torch.linspace(0, t.numel() - 1, n).long().clamp_(max=t.numel() - 1)]
     for k in ("command_logits", "args_logits", "visibility_logits"):
         assert tuple(out[k].shape) == tuple(fx["O_shape_" + k]), k
         got = idx(out[k].detach().cpu(), 4096) if out[k].numel() > 4096 else out[k].detach().cpu().reshape(-1)
@@ -311,7 +311,7 @@ def test_parity_mode_at_the_benchmarked_shape():
     for k in ("command_logits", "args_logits", "visibility_logits"):
         got, ref = out[k].detach().cpu(), ro[k]
         assert got.shape == ref.shape
-        sel = torch.linspace(0, got.numel() - 1, 200_000).long()
+        sel = torch.linspace(0, got.numel() - 1, 200_000, dtype=torch.float64).long().clamp_(max=got.numel() - 1)
         np.testing.assert_allclose(got.reshape(-1)[sel].numpy(), ref.reshape(-1)[sel].numpy(), rtol=1e-3, atol=1e-4,
                                    err_msg=k)
     for k in ("command_logits", "args_logits"):
