@@ -8,9 +8,10 @@ See DESIGN.md / INTEGRATION.md.  There is no CPU fallback: the CUDA library must
 """
 from .config import (Hierarchical, HierarchicalSelfMatching, OneStageOneShot, SketchRNN, Sketchformer,  # noqa: F401
                      _DefaultConfig)
+from .data import PackedBatch, pack_icons, pack_tensors  # noqa: F401
 from .loss import SVGLoss  # noqa: F401
 from .model import SVGTransformer  # noqa: F401
 from .optim import FusedAdamW  # noqa: F401
 
 __all__ = ["SVGTransformer", "SVGLoss", "Hierarchical", "OneStageOneShot", "HierarchicalSelfMatching", "SketchRNN",
-           "Sketchformer", "_DefaultConfig", "FusedAdamW"]
+           "Sketchformer", "_DefaultConfig", "FusedAdamW", "PackedBatch", "pack_icons", "pack_tensors"]

@@ -719,7 +719,10 @@ class SVGTransformer(nn.Module):
         _, w2t = self._pack(pre + ".linear2.weight")
         ops.linear(dx2_act, w2t, M, ff, d, mask=s["h"], mask_scale=1.0 / (1.0 - pff[0]) if pff[0] > 0 else 1.0, out_act=dh)
         ops.outer(dh, s["b"], M, ff, d, G("linear1.weight"), colsum=G("linear1.bias"))
-        fuse = ops.ln_fusable(M, d, pl)
+        # The fused dgrad + LayerNorm-backward kernel (dsvg_linear_ln_bwd) is correct (tests/test_kernels_gpu.py) but measured
+        # SLOWER than the two kernels it replaces (171 vs 147 us at M = 131072, K = 512: its two-pass epilogue is
+        # latency-bound at 18 warps per SM, profiles/README.md), so it is opt-in: DSVG_LN_FUSE_BWD=1.
+        fuse = ops.ln_fusable(M, d, pl) and os.environ.get("DSVG_LN_FUSE_BWD", "0") == "1"
         _, w1t = self._pack(pre + ".linear1.weight")
         dx1 = torch.empty(M, d, device=dev)
         dt = Act(M, d, pl, dev)

@@ -104,6 +104,21 @@ int dsvg_linear_ln_bwd(const dsvg_bf16* dY, size_t dy_lo_off, int lda, const dsv
                        const float* dx_in, float* dx_out, dsvg_bf16* dact, float drop_p, uint32_t drop_site, uint64_t seed,
                        float* dgamma, float* dbeta, void* stream);
 
+/* ---- input side: packed batch format --------------------------------------------- */
+/* HOST function.  Assembles one batch the way SVGTensorDataset.get_data does per icon (svgtensor_dataset.py:164-205 with
+ * SVGTensor.add_eos / add_sos / pad, difflib/tensor.py:108-143) followed by the default collate, directly into the packed
+ * format: cmd_out uint8 [n_icons, G, seq_len+2], args_out int16 [n_icons, G, seq_len+2, 11] (PAD = -1).
+ * rows: the icons' raw (len, 14) path tensors concatenated (14 columns: cmd, rx, ry, phi, fA, fS, x0, y0, c1x, c1y, c2x, c2y,
+ * x, y -- difflib/tensor.py:23-32); group_offsets [n_icons*max_groups + 1]: row offset of every path (missing paths are
+ * empty ranges).  grouped = 0: the per-path tensors (`commands` / `args`, G = max_groups, seq_len = MAX_SEQ_LEN);
+ * grouped = 1: the `_grouped` variants (G = 1, all paths of an icon concatenated, seq_len = MAX_TOTAL_LEN).
+ * Fails (non-zero) where the reference's torch.stack would: a sequence that does not fit the window. */
+int dsvg_pack_icons(const float* rows, const long long* group_offsets, int n_icons, int max_groups, int seq_len, int grouped,
+                    unsigned char* cmd_out, short* args_out);
+/* Device: packed batch -> the float32 tensors the forward consumes (commands [n_positions], args [n_positions, n_args]). */
+int dsvg_unpack_batch(const unsigned char* cmd, const short* args, float* commands_f32, float* args_f32, size_t n_positions,
+                      int n_args, void* stream);
+
 /* ---- sequence bookkeeping (model/utils.py:7-66) ------------------------------------------------------ */
 /* From commands[nseq, L] (ids stored as float): first_eos[nseq], visible[nseq] (#EOS < L-1), key_valid[nseq*L]
  * (1 before the first EOS), grp[nseq*L] (# of "m" so far), counts[2] += {loss_cmd positions, loss_args slots}.

@@ -101,7 +101,8 @@ def param_shapes(cfg):
         out["encoder.label_embedding.label_embedding.weight"] = (cfg.n_labels, cfg.dim_label)
     stack("encoder.encoder", cfg.n_layers, False)
     if two_e:
-        out["encoder.hierarchical_PE.pos_embed.weight"] = (cfg.max_num_groups, d)
+        if not getattr(cfg, "self_match", False):                      # model.py:114-115 (permutation-invariant E2 when matching)
+            out["encoder.hierarchical_PE.pos_embed.weight"] = (cfg.max_num_groups, d)
         stack("encoder.hierarchical_encoder", cfg.n_layers, False)
     if cfg.use_resnet:
         for i in range(1, 5):
@@ -317,7 +318,8 @@ def forward(params, cfg, commands, args, label=None, eps=None, matmul="fp32", z_
         z = (mem * w).sum(-2) / w.sum(-2)                                                 # [N,G,d]
         if two_e:
             vis = visibility(cmd)                                                         # [N,G]
-            z = _drop(z + p["encoder.hierarchical_PE.pos_embed.weight"][:G], dr_pe)        # model.py:158
+            if not getattr(cfg, "self_match", False):
+                z = _drop(z + p["encoder.hierarchical_PE.pos_embed.weight"][:G], dr_pe)    # model.py:157-158
             mem2 = _stack(mm, z, p, "encoder.hierarchical_encoder", cfg.n_layers, H, ~vis, lab=lab_e, drop=dr)   # :160
             wv = vis.to(dt).unsqueeze(-1)
             z = (mem2 * wv).sum(-2) / wv.sum(-2)                                           # :161  [N,d]
@@ -362,8 +364,58 @@ def forward(params, cfg, commands, args, label=None, eps=None, matmul="fp32", z_
     res["command_logits"] = mm.linear(out, p["decoder.fcn.command_fcn.weight"], p["decoder.fcn.command_fcn.bias"])
     al = mm.linear(out, p["decoder.fcn.args_fcn.weight"], p["decoder.fcn.args_fcn.bias"])
     res["args_logits"] = al.reshape(N, Gd, Ld, cfg.n_args, cfg.args_dim + 1)                # basic_blocks.py:21
+    if getattr(cfg, "self_match", False) and two_d and z_in is None:                        # model.py:384-394
+        asg = perfect_matching(res["command_logits"].detach(), res["args_logits"].detach(),
+                               res["visibility_logits"].detach(), commands[..., 1:], args[..., 1:, :], cfg)
+        res["assignment"] = asg
+        for k in ("command_logits", "args_logits", "visibility_logits"):
+            t = res[k]
+            idx = asg.reshape(asg.shape + (1,) * (t.dim() - 2)).expand_as(t)
+            res[k] = torch.gather(t, 1, idx)
     res["tgt_commands"], res["tgt_args"] = commands, args                                  # model.py:404-405
     return res
+
+
+# --------------------------------------------------------------------------------------------------
+# Hungarian self-matching (model.py:311-350, cfg.self_match; model/config.py:101-108)
+# --------------------------------------------------------------------------------------------------
+def matching_costs(cl, al, vl, tgt_c, tgt_a):
+    """cost[n, g, p] of explaining target path g with predicted slot p (model.py:313-337): 2 * masked-mean args CE +
+    masked-mean command CE + visibility CE.  tgt_c / tgt_a are the SHIFTED targets (commands[..., 1:], args[..., 1:, :]), and
+    -- as in the reference -- visibility and the extended padding mask are taken on those shifted sequences (so a path of a
+    single command counts as invisible here, unlike in the loss).  Also returns the visibility mask [N, G]."""
+    N, G, S, na = tgt_a.shape
+    Gp = cl.shape[1]
+    tc = tgt_c.long()
+    vis = (tc == CMD_EOS).sum(-1) < S - 1                                                   # model/utils.py:45-56
+    pad = extended_padding(tc).to(cl.dtype) * vis.unsqueeze(-1).to(cl.dtype)                # model.py:315
+    lc_all = F.log_softmax(cl, -1)[:, None].expand(N, G, Gp, S, cl.shape[-1])
+    la_all = F.log_softmax(al, -1)[:, None].expand(N, G, Gp, S, na, al.shape[-1])
+    lv_all = F.log_softmax(vl.reshape(N, Gp, 2), -1)[:, None].expand(N, G, Gp, 2)
+    ce_c = -lc_all.gather(-1, tc[:, :, None, :, None].expand(N, G, Gp, S, 1)).squeeze(-1)
+    ce_a = -la_all.gather(-1, (tgt_a.long() + 1)[:, :, None, :, :, None].expand(N, G, Gp, S, na, 1)).squeeze(-1)
+    ce_v = -lv_all.gather(-1, vis.long()[:, :, None, None].expand(N, G, Gp, 1)).squeeze(-1)
+    mask = CMD_ARGS_MASK.to(tc.device)[tc].to(cl.dtype)                                     # [N,G,S,na]
+    la = (ce_a * mask[:, :, None]).sum((-1, -2)) / mask.sum((-1, -2))[:, :, None]           # :334
+    lc = (ce_c * pad[:, :, None]).sum(-1) / pad.sum(-1)[:, :, None]                         # :335
+    return 2.0 * la + 1.0 * lc + 1.0 * ce_v, vis                                            # :337
+
+
+def perfect_matching(cl, al, vl, tgt_c, tgt_a, cfg):
+    """model.py:311-350.  Returns assignment [N, Gp] (long): output slot i of icon n takes predicted slot assignment[n, i].
+    Rows of the cost matrix are the VISIBLE targets in order (compacted, costs[mask]); the unassigned slots follow in
+    ascending order (`assign + list(full_set - set(assign))`).  The optimal assignment itself comes from the reference's own
+    third-party solver, scipy.optimize.linear_sum_assignment (model.py:13,344)."""
+    from scipy.optimize import linear_sum_assignment
+    with torch.no_grad():
+        cost, vis = matching_costs(cl, al, vl, tgt_c, tgt_a)
+    Gp = cfg.num_groups_proposal
+    rows = []
+    for i in range(cost.shape[0]):
+        _, assign = linear_sum_assignment(cost[i][vis[i]].cpu())
+        assign = assign.tolist()
+        rows.append(assign + sorted(set(range(Gp)) - set(assign)))
+    return torch.tensor(rows, device=cl.device)
 
 
 # --------------------------------------------------------------------------------------------------

@@ -25,7 +25,8 @@ for m in ["tensorboardX", "cairosvg", "IPython", "IPython.display", "moviepy", "
 
 from deepsvg.model import loss as ref_loss_mod          # noqa: E402
 from deepsvg.model import utils as ref_utils            # noqa: E402
-from deepsvg.model.config import Hierarchical, OneStageOneShot  # noqa: E402
+from deepsvg.model import model as ref_model_mod        # noqa: E402
+from deepsvg.model.config import Hierarchical, HierarchicalSelfMatching, OneStageOneShot  # noqa: E402
 from deepsvg.model.loss import SVGLoss                  # noqa: E402
 from deepsvg.model.model import SVGTransformer          # noqa: E402
 
@@ -46,6 +47,7 @@ def dealiased_padding_mask(commands, seq_dim=0, extended=False):
 
 
 ref_loss_mod._get_padding_mask = dealiased_padding_mask
+ref_model_mod._get_padding_mask = dealiased_padding_mask      # perfect_matching (model.py:315) uses the same aliased add
 
 CASES = {
     # name: (kind, overrides, batch, store_full)
@@ -74,6 +76,12 @@ CASES = {
                                          max_seq_len=64), 2, False),
     # BASELINE.json configs[3] (one-stage fonts): G = 1 grouped tensors of 50 commands, 52 labels, VAE
     "fonts_cfg4": ("one_stage", dict(use_vae=True, label_condition=True, n_labels=52, max_total_len=50), 3, False),
+    # HierarchicalSelfMatching (model/config.py:101-108): Hungarian assignment of predicted slots to target paths
+    "tiny_selfmatch": ("hierarchical", dict(d_model=32, n_heads=4, dim_feedforward=64, dim_z=24, n_layers=2,
+                                            n_layers_decode=2, max_num_groups=4, max_seq_len=6, args_dim=15,
+                                            use_vae=False, self_match=True), 5, True),
+    "selfmatch_d128": ("hierarchical", dict(use_vae=False, d_model=128, n_heads=4, dim_feedforward=256, dim_z=64, n_layers=2,
+                                            n_layers_decode=2, max_num_groups=4, max_seq_len=10, self_match=True), 6, False),
 }
 
 
@@ -110,7 +118,7 @@ WEIGHTS = dict(O.DEFAULT_WEIGHTS)
 
 
 def ref_cfg(kind, over):
-    c = Hierarchical() if kind == "hierarchical" else OneStageOneShot()
+    c = (HierarchicalSelfMatching() if over.get("self_match") else Hierarchical()) if kind == "hierarchical" else OneStageOneShot()
     for k, v in over.items():
         setattr(c, k, v)
     if "max_total_len" not in over:
@@ -155,6 +163,14 @@ def run_case(name):
         eps = torch.randn(batch, cfg_o.dim_z, generator=torch.Generator().manual_seed(6)).double()
         real = torch.randn_like
         torch.randn_like = lambda s, *a, **k: eps.reshape(s.shape).to(s.dtype)
+    captured = {}
+    if getattr(cfg_r, "self_match", False):
+        orig_pm = model.perfect_matching
+
+        def spy(*a):
+            captured["asg"] = orig_pm(*a)
+            return captured["asg"]
+        model.perfect_matching = spy
     try:
         out = model(cmd, arg, cmd, arg, params={}, **kw)
     finally:
@@ -166,6 +182,8 @@ def run_case(name):
     grads = {k: (p.grad if p.grad is not None else torch.zeros_like(p)) for k, p in model.named_parameters()}
 
     fx = {"commands": cmd.float().numpy(), "args": arg.float().numpy(), "seed_params": np.int64(7)}
+    if captured:
+        fx["assignment"] = captured["asg"].reshape(batch, -1).numpy()     # what the reference's perfect_matching picked
     if label is not None:
         fx["label"] = label.numpy()
     if eps is not None:

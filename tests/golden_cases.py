@@ -29,6 +29,12 @@ CASES = {
     "scaled_cfg5": ("hierarchical", dict(use_vae=False, d_model=512, n_layers=8, n_layers_decode=8, max_num_groups=16,
                                          max_seq_len=64), False),
     "fonts_cfg4": ("one_stage", dict(use_vae=True, label_condition=True, n_labels=52, max_total_len=50), False),
+    # HierarchicalSelfMatching (model/config.py:101-108)
+    "tiny_selfmatch": ("hierarchical", dict(d_model=32, n_heads=4, dim_feedforward=64, dim_z=24, n_layers=2,
+                                            n_layers_decode=2, max_num_groups=4, max_seq_len=6, args_dim=15,
+                                            use_vae=False, self_match=True), True),
+    "selfmatch_d128": ("hierarchical", dict(use_vae=False, d_model=128, n_heads=4, dim_feedforward=256, dim_z=64, n_layers=2,
+                                            n_layers_decode=2, max_num_groups=4, max_seq_len=10, self_match=True), False),
 }
 
 

@@ -39,6 +39,9 @@ def test_oracle_matches_reference(name):
             assert abs(losses[k].item() - float(fx["L_" + k])) <= 1e-10 * max(1.0, abs(float(fx["L_" + k]))), k
         else:
             assert k not in losses
+    if "assignment" in fx:      # HierarchicalSelfMatching: the Hungarian assignment itself (model.py:339-350)
+        assert out["assignment"].tolist() == fx["assignment"].tolist()
+        assert any(row != sorted(row) for row in fx["assignment"].tolist()), "fixture must contain a non-identity assignment"
     assert sorted(grads) == list(fx["param_names"])
     for k, g in grads.items():
         got = g if full else _strided(g, 512)
