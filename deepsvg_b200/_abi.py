@@ -24,6 +24,8 @@ SIGNATURES = {
     "dsvg_linear_ln_bwd": (I, [P, Z, I, P, Z, I, I, I, I, P, P, P, P, P, P, P] + DROP + [P, P, P]),
     "dsvg_pack_icons": (I, [P, P, I, I, I, I, P, P]),
     "dsvg_unpack_batch": (I, [P, P, P, P, Z, I, P]),
+    "dsvg_match_assign": (I, [P, I, P, I, I, I, P, P, P, I, I, I, I, P, P, P, P, P, P]),
+    "dsvg_permute_groups": (I, [P, P, P, I, I, Z, I, P]),
     "dsvg_seq_prep": (I, [P, I, I, P, P, P, P, P, P]),
     "dsvg_embed_fold": (I, [P, P, P, P, P, I, I, I, P]),
     "dsvg_embed_fwd": (I, [P, P, P, P, P, P, P, P, P, I, I, I, I, I] + DROP + [P]),

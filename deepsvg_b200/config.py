@@ -45,7 +45,7 @@ class Hierarchical(_DefaultConfig):             # model/config.py:92-98
     VARIANT = dict(encode_stages=2, decode_stages=2)
 
 
-class HierarchicalSelfMatching(_DefaultConfig):  # model/config.py:101-108 (rejected by check_supported)
+class HierarchicalSelfMatching(_DefaultConfig):  # model/config.py:101-108
     VARIANT = dict(encode_stages=2, decode_stages=2, self_match=True)
 
 
@@ -66,8 +66,10 @@ def check_supported(cfg):
         raise NotImplementedError("deepsvg_b200: pred_mode='autoregressive' is outside the accelerated path")
     if getattr(cfg, "rel_targets", False):
         raise NotImplementedError("deepsvg_b200: rel_targets=True is outside the accelerated path")
-    if getattr(cfg, "self_match", False):
-        raise NotImplementedError("deepsvg_b200: self_match=True (Hungarian assignment) is outside the accelerated path")
+    if getattr(cfg, "self_match", False) and not (cfg.encode_stages == 2 and cfg.decode_stages == 2):
+        raise NotImplementedError("deepsvg_b200: self_match=True expects the two-stage model (model.py:385)")
+    if getattr(cfg, "self_match", False) and (cfg.num_groups_proposal > 16 or cfg.max_num_groups > cfg.num_groups_proposal):
+        raise NotImplementedError("deepsvg_b200: self_match needs max_num_groups <= num_groups_proposal <= 16")
     if cfg.encode_stages not in (1, 2) or cfg.decode_stages not in (1, 2) or cfg.encode_stages != cfg.decode_stages:
         raise NotImplementedError("deepsvg_b200: encode_stages and decode_stages must both be 1 or both be 2")
     if cfg.d_model % 128 != 0 or cfg.d_model > 512:

@@ -85,7 +85,8 @@ def _param_specs(cfg):
         S.append(("encoder.label_embedding.label_embedding.weight", (cfg.n_labels, cfg.dim_label), "kaiming"))
     stack("encoder.encoder", cfg.n_layers, False)
     if two:
-        S.append(("encoder.hierarchical_PE.pos_embed.weight", (cfg.max_num_groups, d), "kaiming"))
+        if not getattr(cfg, "self_match", False):        # model.py:114-115: no positional code over paths when self-matching
+            S.append(("encoder.hierarchical_PE.pos_embed.weight", (cfg.max_num_groups, d), "kaiming"))
         stack("encoder.hierarchical_encoder", cfg.n_layers, False)
     if cfg.use_resnet:
         for i in range(1, 5):
@@ -236,8 +237,10 @@ class SVGTransformer(nn.Module):
         dec_len = (cfg.max_seq_len if two else cfg.max_total_len) + 1
         pos = lambda n: torch.arange(0, n, dtype=torch.long).unsqueeze(1)   # positional_encoding.py:30-31
         _register(self, "encoder.embedding.pos_encoding.position", pos(enc_len), True)
+        self.self_match = bool(getattr(cfg, "self_match", False))
         if two:
-            _register(self, "encoder.hierarchical_PE.position", pos(cfg.max_num_groups), True)
+            if not self.self_match:
+                _register(self, "encoder.hierarchical_PE.position", pos(cfg.max_num_groups), True)
             _register(self, "decoder.hierarchical_embedding.PE.position", pos(cfg.num_groups_proposal), True)
         _register(self, "decoder.embedding.PE.position", pos(dec_len), True)
         self.register_buffer("cmd_args_mask", CMD_ARGS_MASK.clone())       # model.py:309
@@ -271,7 +274,10 @@ class SVGTransformer(nn.Module):
         """model.py:352-412.  Tensors are batch-first float32 CUDA tensors: commands (N, G, S+2), args (N, G, S+2, 11)."""
         cfg = self.cfg
         if hierarch_logits is not None:
-            raise NotImplementedError("deepsvg_b200: forward(hierarch_logits=...) is not on the accelerated path")
+            # model.py:246-259: the per-path stage was run before (return_hierarch=True); `z` now holds the PER-PATH latents,
+            # batch-first (N, Gp, 1, dz), and hierarch_logits the visibility logits as that call returned them (1, Gp, N, 2)
+            if z is None or cfg.decode_stages != 2 or torch.is_grad_enabled() and z.requires_grad:
+                raise ValueError("forward(hierarch_logits=...) needs the two-stage model, z = per-path latents, and no grad")
         if z is None and (commands_enc is None or args_enc is None):
             raise ValueError("encoder inputs are required when z is not given")
         ref = commands_enc if commands_enc is not None else z
@@ -287,11 +293,15 @@ class SVGTransformer(nn.Module):
             if os.environ.get("DSVG_DEBUG_CHECKS") and (int(label.min()) < 0 or int(label.max()) >= cfg.n_labels):
                 raise ValueError("label ids must lie in [0, n_labels)")
         inputs = dict(commands=commands_enc, args=args_enc, label=label, z=z, encode_mode=encode_mode,
-                      return_hierarch=return_hierarch, training=self.training)
+                      return_hierarch=return_hierarch, training=self.training, hierarch_logits=hierarch_logits)
+        if self.self_match and return_tgt and not encode_mode and not return_hierarch:   # model.py:384
+            if commands_dec is None or args_dec is None:
+                raise ValueError("self_match needs the decoder targets (commands_dec, args_dec)")
+            inputs["match_targets"] = (commands_dec.detach().contiguous().float(), args_dec.detach().contiguous().float())
         plist = [self._param(n) for n in self._pnames]
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in plist)
         token = torch.zeros((), device=ref.device, requires_grad=need_grad)
-        need_grad = need_grad and not return_hierarch          # return_hierarch is an inference-only exit
+        need_grad = need_grad and not return_hierarch and hierarch_logits is None   # inference-only exits
         inputs["need_grad"] = need_grad
         tgt_prep = None
         if need_grad and self.process_group is not None and return_tgt and commands_dec is not None and not encode_mode:
@@ -577,9 +587,12 @@ class SVGTransformer(nn.Module):
                             sv.e1_mean, sv.e1_rstd, sv.e1_icnt, nseq, L, d)
             if two:
                 # ---- E2 (model.py:153-162): sequences of G path codes per icon ----
-                x = torch.empty(nseq, d, device=dev)
-                ops.rows_embed_fwd(zp, P("encoder.hierarchical_PE.pos_embed.weight"), x, nseq, G, d,
-                                   self._drop(sv, "enc.pe2", 0.1))
+                if self.self_match:                      # model.py:157: the path codes enter E2 as they are
+                    x = zp
+                else:
+                    x = torch.empty(nseq, d, device=dev)
+                    ops.rows_embed_fwd(zp, P("encoder.hierarchical_PE.pos_embed.weight"), x, nseq, G, d,
+                                       self._drop(sv, "enc.pe2", 0.1))
                 x, _ = self._stack_fwd(sv, "encoder.hierarchical_encoder", cfg.n_layers, x, nseq, G, N, sv.visible,
                                        lab=lab_e, lab_rows_per_group=G)
                 sv.e2_x = x
@@ -625,10 +638,13 @@ class SVGTransformer(nn.Module):
             zin = inp["z"]
             N = zin.shape[0]
             dev = zin.device
-            zl = zin.reshape(N, dz).contiguous().float()                        # batch-first (N,1,1,dz), model.py:369
-            z_act = Act(N, dz, pl, dev)
-            ops.cast_act(zl, N, dz, out=z_act)
             sv.N = N
+            if inp.get("hierarch_logits") is not None:
+                zl = z_act = None                                               # the icon-level latent is not needed
+            else:
+                zl = zin.reshape(N, dz).contiguous().float()                    # batch-first (N,1,1,dz), model.py:369
+                z_act = Act(N, dz, pl, dev)
+                ops.cast_act(zl, N, dz, out=z_act)
         sv.z32, sv.z_act = zl, z_act
         if inp["encode_mode"]:
             return [zl], sv
@@ -640,7 +656,15 @@ class SVGTransformer(nn.Module):
             ops.gather_rows(P("decoder.label_embedding.label_embedding.weight"), label, N, cfg.dim_label, lab_d)
         sv.lab_d = lab_d
         outs = []
-        if two:
+        if two and inp.get("hierarch_logits") is not None:
+            Gp = cfg.num_groups_proposal
+            nq = N * Gp
+            zp32 = inp["z"].reshape(nq, dz).contiguous().float()
+            zp_act = Act(nq, dz, pl, dev)
+            ops.cast_act(zp32, nq, dz, out=zp_act)
+            vis_logits = inp["hierarch_logits"].reshape(Gp, N, 2).permute(1, 0, 2).contiguous().float().view(nq, 2)
+            zmem, nseq_d, lab_rpg = zp_act, nq, Gp
+        elif two:
             Gp = cfg.num_groups_proposal
             nq = N * Gp
             x = torch.empty(nq, d, device=dev)
@@ -692,6 +716,29 @@ class SVGTransformer(nn.Module):
         args_logits = torch.empty(Md, na_out, device=dev)
         w, _ = self._pack("decoder.fcn.args_fcn.weight")
         ops.linear(y, w, Md, na_out, d, bias=P("decoder.fcn.args_fcn.bias"), out_f32=args_logits)  # basic_blocks.py:20
+        if inp.get("match_targets") is not None:
+            # ---- Hungarian self-matching (model.py:384-394): pick, per icon, which predicted slot explains which target
+            # path, then emit the logits in that order.  The permutation is applied to the decoder rows (67 MB) and the two
+            # heads run again on the permuted rows -- the same cost as gathering the 1.4 GB logits tensor, and the backward
+            # pass then only has to scatter the head input gradients back.
+            tc, ta = inp["match_targets"]
+            Gt, Gp = tc.shape[1], cfg.num_groups_proposal
+            asg, sv.match_cost, _ = ops.match_assign(cmd_logits, args_logits, na_out, vis_logits, tc, ta, N, Gt, Gp, Ld + 1,
+                                                     cfg.n_args, self.args_dim)
+            sv.asg = asg
+            y_perm = Act(Md, d, pl, dev)
+            ops.permute_act(y, y_perm, asg, N, Gp, Ld)
+            sv.d1_y = y_perm
+            w, _ = self._pack("decoder.fcn.command_fcn.weight")
+            ops.linear(y_perm, w, Md, nc, d, bias=P("decoder.fcn.command_fcn.bias"), out_f32=cmd_logits)
+            w, _ = self._pack("decoder.fcn.args_fcn.weight")
+            ops.linear(y_perm, w, Md, na_out, d, bias=P("decoder.fcn.args_fcn.bias"), out_f32=args_logits)
+            y2_perm = Act(nq, d, pl, dev)
+            ops.permute_act(sv.d2_y, y2_perm, asg, N, Gp, 1)
+            sv.d2_y_perm = y2_perm
+            vis_perm = torch.empty_like(vis_logits)
+            ops.permute_groups(vis_logits, vis_perm, asg, N, Gp, 8)
+            vis_logits = vis_perm
         outs = [cmd_logits, args_logits]
         if two:
             outs.append(vis_logits)
@@ -873,6 +920,10 @@ class SVGTransformer(nn.Module):
             dy32 = torch.zeros(Md, d, device=dev)
             self._head_bwd(gd, "decoder.fcn.args_fcn", src_args, sv.d1_y, Md, na_out, d, dy32)
             self._head_bwd(gd, "decoder.fcn.command_fcn", src_cmd, sv.d1_y, Md, nc, d, dy32)
+            asg = getattr(sv, "asg", None)
+            if asg is not None:      # the heads saw the slot-permuted rows: scatter their input gradient back (gather backward)
+                dy32_p, dy32 = dy32, torch.empty(Md, d, device=dev)
+                ops.permute_groups(dy32_p, dy32, asg, N, cfg.num_groups_proposal, Ld * d * 4, inverse=True)
             dy = Act(Md, d, pl, dev)
             ops.cast_act(dy32, Md, d, out=dy)
             nl = cfg.n_layers_decode
@@ -898,7 +949,15 @@ class SVGTransformer(nn.Module):
                 ops.cast_act(dzp32, nq, dz, out=dzp)
                 dy32 = torch.zeros(nq, d, device=dev)
                 self._head_bwd(gd, "decoder.hierarchical_fcn.z_fcn", [(dzp, None)], sv.d2_y, nq, dz, d, dy32)
-                self._head_bwd(gd, "decoder.hierarchical_fcn.visibility_fcn", src_vis, sv.d2_y, nq, 2, d, dy32)
+                if asg is not None and src_vis:
+                    dyv_p, dyv = torch.zeros(nq, d, device=dev), torch.empty(nq, d, device=dev)
+                    self._head_bwd(gd, "decoder.hierarchical_fcn.visibility_fcn", src_vis, sv.d2_y_perm, nq, 2, d, dyv_p)
+                    ops.permute_groups(dyv_p, dyv, asg, N, Gp, d * 4, inverse=True)
+                    dsum = torch.empty(nq, d, device=dev)
+                    ops.add_f32(dy32, dyv, dsum)
+                    dy32 = dsum
+                else:
+                    self._head_bwd(gd, "decoder.hierarchical_fcn.visibility_fcn", src_vis, sv.d2_y, nq, 2, d, dy32)
                 dy = Act(nq, d, pl, dev)
                 ops.cast_act(dy32, nq, d, out=dy)
                 dx, dxa = torch.empty(nq, d, device=dev), Act(nq, d, pl, dev)
@@ -964,9 +1023,12 @@ class SVGTransformer(nn.Module):
                            dbeta=gd["encoder.hierarchical_encoder.norm.bias"])
                 dx = self._stack_bwd(sv, gd, "encoder.hierarchical_encoder", nl, dx, dxa, nseq, G, N, sv.visible,
                                      lab=sv.lab_e, dlab=dlab_e, lab_rows_per_group=G)
-                dzp = torch.empty(nseq, d, device=dev)
-                ops.rows_embed_bwd(dx, dzp, gd["encoder.hierarchical_PE.pos_embed.weight"], N, G, d,
-                                   self._drop(sv, "enc.pe2", 0.1))
+                if self.self_match:
+                    dzp = dx
+                else:
+                    dzp = torch.empty(nseq, d, device=dev)
+                    ops.rows_embed_bwd(dx, dzp, gd["encoder.hierarchical_PE.pos_embed.weight"], N, G, d,
+                                       self._drop(sv, "enc.pe2", 0.1))
             else:
                 dzp = dzin
             dx, dxa = torch.empty(M1, d, device=dev), Act(M1, d, pl, dev)
@@ -993,7 +1055,7 @@ class SVGTransformer(nn.Module):
     # =================================================================================================
     def _graph_key(self, inp):
         """Input signature a captured graph is valid for, or None when this call is not graphable."""
-        if not self.graphs or not inp["training"] or not inp.get("need_grad", False) or inp["z"] is not None \
+        if not self.graphs or self.self_match or not inp["training"] or not inp.get("need_grad", False) or inp["z"] is not None \
                 or inp["encode_mode"] or inp["return_hierarch"] or ops.PROFILE is not None:
             return None
         c, a, lab = inp["commands"], inp["args"], inp["label"]

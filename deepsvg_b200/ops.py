@@ -290,3 +290,37 @@ def scatter_rows(g, idx, n, w, dtable):
 def add_f32(a, b, y):
     rc = _lib.load().dsvg_add_f32(a.data_ptr(), b.data_ptr(), y.data_ptr(), y.numel(), _stream())
     _lib.check(rc, "dsvg_add_f32")
+
+
+def match_assign(cmd_logits, args_logits, ld_args, vis_logits, commands, args, N, G, Gp, L, n_args, n_classes):
+    """Hungarian self-matching (model.py:311-350) on the GPU: returns (assignment int64 [N, Gp], cost fp64 [N, G, Gp],
+    visible uint8 [N, G])."""
+    dev = cmd_logits.device
+    n_tok = N * Gp * (L - 1)
+    lse_c = torch.empty(n_tok, device=dev)
+    lse_a = torch.empty(n_tok * n_args, device=dev)
+    cost = torch.empty(N, G, Gp, dtype=torch.float64, device=dev)
+    vis = torch.empty(N, G, dtype=torch.uint8, device=dev)
+    asg = torch.empty(N, Gp, dtype=torch.int64, device=dev)
+    rc = _lib.load().dsvg_match_assign(cmd_logits.data_ptr(), cmd_logits.shape[-1], args_logits.data_ptr(), ld_args, n_args,
+                                       n_classes, vis_logits.data_ptr(), commands.data_ptr(), args.data_ptr(), N, G, Gp, L,
+                                       lse_c.data_ptr(), lse_a.data_ptr(), cost.data_ptr(), vis.data_ptr(), asg.data_ptr(),
+                                       _stream())
+    _lib.check(rc, "dsvg_match_assign")
+    return asg, cost, vis
+
+
+def permute_groups(src, dst, asg, N, G, group_bytes, inverse=False):
+    """dst group (n, i) = src group (n, asg[n, i]) (or the inverse scatter); src / dst: tensors or raw pointers."""
+    sp = src if isinstance(src, int) else src.data_ptr()
+    dp = dst if isinstance(dst, int) else dst.data_ptr()
+    rc = _lib.load().dsvg_permute_groups(sp, dp, asg.data_ptr(), N, G, group_bytes, 1 if inverse else 0, _stream())
+    _lib.check(rc, "dsvg_permute_groups")
+
+
+def permute_act(src, dst, asg, N, G, rows_per_group, inverse=False):
+    """Group permutation of an Act (every plane)."""
+    gb = rows_per_group * src.ld * 2
+    for pl in range(src.planes):
+        off = pl * src.rows * src.ld * 2
+        permute_groups(src.ptr + off, dst.ptr + off, asg, N, G, gb, inverse)

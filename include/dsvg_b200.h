@@ -119,6 +119,23 @@ int dsvg_pack_icons(const float* rows, const long long* group_offsets, int n_ico
 int dsvg_unpack_batch(const unsigned char* cmd, const short* args, float* commands_f32, float* args_f32, size_t n_positions,
                       int n_args, void* stream);
 
+/* ---- Hungarian self-matching (cfg.self_match) -------------------------------------- */
+/* SVGTransformer.perfect_matching, model.py:311-350, without the host round trip: cost[N, G, Gp] (fp64) = 2 * masked-mean
+ * CE_args + masked-mean CE_cmd + CE_visibility between target path g (the SHIFTED targets commands[..., 1:], args[..., 1:, :],
+ * read from the unshifted commands [N*G, L] / args [N*G, L, n_args]) and predicted slot p; visible[N*G]; then one thread per
+ * icon solves the assignment over its visible targets (replacing scipy.optimize.linear_sum_assignment, model.py:344) and
+ * writes assignment[N, Gp] exactly as the reference lists it: slot of the i-th visible target, then the unused slots in
+ * ascending order.  lse_cmd [N*Gp*(L-1)], lse_args [N*Gp*(L-1)*n_args] are scratch. */
+int dsvg_match_assign(const float* cmd_logits, int n_cmd, const float* args_logits, int ld_args, int n_args, int n_classes,
+                      const float* vis_logits, const float* commands, const float* args, int N, int G, int Gp, int L,
+                      float* lse_cmd, float* lse_args, double* cost, unsigned char* visible, long long* assignment,
+                      void* stream);
+/* torch.gather along the slot axis (model.py:389-391) as a group-granular copy: dst group (n, i) = src group
+ * (n, assignment[n, i]); inverse != 0 scatters instead (the backward of the gather).  A group is group_bytes contiguous
+ * bytes (multiple of 4): L * row bytes of one slot's tokens. */
+int dsvg_permute_groups(const void* src, void* dst, const long long* assignment, int N, int G, size_t group_bytes,
+                        int inverse, void* stream);
+
 /* ---- sequence bookkeeping (model/utils.py:7-66) ------------------------------------------------------ */
 /* From commands[nseq, L] (ids stored as float): first_eos[nseq], visible[nseq] (#EOS < L-1), key_valid[nseq*L]
  * (1 before the first EOS), grp[nseq*L] (# of "m" so far), counts[2] += {loss_cmd positions, loss_args slots}.

@@ -15,6 +15,7 @@ def _mk(kind, over):
 
 
 @pytest.mark.parametrize("kind,over", [("hierarchical", dict(use_vae=False)),
+                                       ("hierarchical", dict(use_vae=False, self_match=True)),
                                        ("hierarchical", dict(label_condition=True, n_labels=62, dim_z=128)),
                                        ("one_stage", dict(label_condition=True, n_labels=52, max_total_len=50))])
 def test_parameter_inventory_matches_oracle_and_reference_names(kind, over):
@@ -56,11 +57,26 @@ def test_config_mirror_and_model_args():
 
 
 @pytest.mark.parametrize("over", [dict(model_type="lstm"), dict(pred_mode="autoregressive"), dict(rel_targets=True),
-                                  dict(self_match=True), dict(d_model=192), dict(encode_stages=2, decode_stages=1)])
+                                  dict(self_match=True, num_groups_proposal=20, max_num_groups=20), dict(d_model=192),
+                                  dict(encode_stages=2, decode_stages=1)])
 def test_unsupported_variants_raise_at_construction(over):
     from deepsvg_b200 import Hierarchical, SVGTransformer
     with pytest.raises(NotImplementedError):
         SVGTransformer(Hierarchical(**over))
+
+
+def test_self_matching_variant_is_constructible_and_has_no_path_positional_code():
+    """model/config.py:101-108, model.py:114-115."""
+    from deepsvg_b200 import HierarchicalSelfMatching, OneStageOneShot, SVGTransformer
+    m = SVGTransformer(HierarchicalSelfMatching(use_vae=False))
+    names = dict(m.named_parameters())
+    assert "encoder.hierarchical_PE.pos_embed.weight" not in names and "decoder.hierarchical_embedding.PE.pos_embed.weight" in names
+    cfg, fx, _ = load_case("selfmatch_d128")
+    from deepsvg_b200.config import _DefaultConfig
+    m2 = SVGTransformer(_DefaultConfig(**vars(cfg)))
+    assert sorted(k for k, _ in m2.named_parameters()) == list(fx["param_names"])     # names read from the real reference
+    with pytest.raises(NotImplementedError):
+        SVGTransformer(OneStageOneShot(self_match=True, max_total_len=50))
 
 
 def test_golden_cases_cover_all_reference_branches():

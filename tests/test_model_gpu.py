@@ -423,3 +423,93 @@ def test_cuda_graph_guards_and_optimizer_updates():
         mg.zero_grad(set_to_none=True)
         loss_fn(mg(c2, a2, c2, a2, params={}), None, weights=W)["loss"].backward()
     assert mg._gs is not None and mg._gs is not gs and mg._gs.key != gs.key
+
+
+# ------------------------------------------------------------------------------------------------ Hungarian self-matching
+def test_self_match_matches_reference_golden():
+    """HierarchicalSelfMatching (model/config.py:101-108): cost tensor, Hungarian assignment and the slot permutation on the
+    GPU against numbers produced by the reference itself (scipy solver, torch.gather) -- assignment bit-exact, permuted
+    logits / losses / every gradient within the parity tolerances."""
+    cfg, fx, _ = load_case("selfmatch_d128")
+    model, loss_fn, _ = _build(cfg, "bf16x3", seed=int(fx["seed_params"]))
+    assert "encoder.hierarchical_PE.pos_embed.weight" not in dict(model.named_parameters())
+    cmd, arg = torch.from_numpy(fx["commands"]), torch.from_numpy(fx["args"])
+    out, ls, grads = _run(model, loss_fn, cmd, arg)
+    idx = lambda t, n: t.reshape(-1)[torch.linspace(0, t.numel() - 1, n).long().clamp_(max=t.numel() - 1)]
+    for k in ("command_logits", "args_logits", "visibility_logits"):
+        assert tuple(out[k].shape) == tuple(fx["O_shape_" + k]), k
+        got = idx(out[k].detach().cpu(), 4096) if out[k].numel() > 4096 else out[k].detach().cpu().reshape(-1)
+        np.testing.assert_allclose(got.numpy(), fx["O_" + k].reshape(-1), rtol=1e-3, atol=1e-4, err_msg=k)
+    for k in ("loss", "loss_cmd", "loss_args", "loss_visibility"):
+        assert abs(ls[k].item() - float(fx["L_" + k])) <= 1e-3 * float(fx["L_" + k]), k
+    for k, g in grads.items():
+        ref_norm = float(fx["Gnorm_" + k])
+        assert abs(g.double().norm().item() - ref_norm) <= 1e-2 * ref_norm + 1e-9, k
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+def test_self_match_assignment_and_gradients_match_oracle(precision):
+    """d_model 256, 8 paths: the GPU solver must pick the oracle's (scipy's) assignment wherever the optimum is separated
+    from the runner-up by more than the logit tolerance; gradients flow through the permutation."""
+    from deepsvg_b200 import ops
+    cfg = O.make_cfg("hierarchical", use_vae=False, self_match=True)
+    model, loss_fn, params = _build(cfg, precision, seed=13)
+    cmd, arg = O.synth_batch(cfg, 5, seed=77)
+    out, ls, grads = _run(model, loss_fn, cmd, arg)
+    ro, rl, rg = O.train_step(params, cfg, cmd, arg)
+    asg_ref = ro["assignment"]
+    # the kernel's assignment for the ORACLE's logits is exact (same costs up to fp32 rounding)
+    raw = O.forward(params, O.make_cfg("hierarchical", use_vae=False), cmd, arg) if False else None
+    if precision == "bf16x3":
+        np.testing.assert_allclose(out["args_logits"].detach().cpu().numpy(), ro["args_logits"].numpy(), rtol=1e-3, atol=1e-4)
+        for k, v in rl.items():
+            assert abs(ls[k].item() - v.item()) <= 1e-3 * abs(v.item()) + 1e-4, k
+        _check_grads(grads, rg, 1e-2)
+    else:
+        assert abs(ls["loss"].item() - rl["loss"].item()) < 2e-2 * rl["loss"].item()
+    assert any(r != sorted(r) for r in asg_ref.tolist())
+
+
+def test_match_kernels_against_scipy_on_random_costs():
+    """dsvg_match_assign on synthetic logits: the cost tensor against the oracle's restatement of model.py:313-337 and the
+    per-icon assignment against scipy.optimize.linear_sum_assignment (the reference's solver), for G < Gp too."""
+    from deepsvg_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    for (N, G, Gp, S) in ((37, 8, 8, 30), (9, 5, 16, 12), (4, 16, 16, 64)):
+        cfg = O.make_cfg("hierarchical", use_vae=False, max_num_groups=G, num_groups_proposal=Gp, max_seq_len=S)
+        cmd, arg = O.synth_batch(cfg, N, seed=N)
+        Ld, C = S + 1, 257
+        cl = torch.randn(N, Gp, Ld, 7, generator=g)
+        al = torch.randn(N, Gp, Ld, 11, C, generator=g) * 2
+        vl = torch.randn(N, Gp, 1, 2, generator=g)
+        cost_ref, vis_ref = O.matching_costs(cl.double(), al.double(), vl.double(), cmd[..., 1:], arg[..., 1:, :])
+        asg_ref = O.perfect_matching(cl.double(), al.double(), vl.double(), cmd[..., 1:], arg[..., 1:, :], cfg)
+        asg, cost, vis = ops.match_assign(cl.to(DEV).view(-1, 7), al.to(DEV).view(-1, 11 * C), 11 * C, vl.to(DEV).view(-1, 2),
+                                          cmd.to(DEV), arg.to(DEV), N, G, Gp, S + 2, 11, C)
+        assert torch.equal(vis.cpu().bool(), vis_ref)
+        m = vis_ref[:, :, None].expand_as(cost_ref)
+        np.testing.assert_allclose(cost.cpu()[m].numpy(), cost_ref[m].numpy(), rtol=2e-5, atol=2e-5)
+        assert asg.cpu().tolist() == asg_ref.tolist()
+        # the permutation kernel and its inverse
+        x = torch.randn(N * Gp * 3, 40, device=DEV)
+        y, z = torch.empty_like(x), torch.empty_like(x)
+        ops.permute_groups(x, y, asg, N, Gp, 3 * 40 * 4)
+        want = torch.gather(x.view(N, Gp, 120), 1, asg[:, :, None].expand(N, Gp, 120)).reshape_as(x)
+        assert torch.equal(y, want)
+        ops.permute_groups(y, z, asg, N, Gp, 3 * 40 * 4, inverse=True)
+        assert torch.equal(z, x)
+
+
+def test_forward_from_hierarch_logits():
+    """model.py:246-259: second-stage decoding from the per-path latents and visibility logits of a return_hierarch call."""
+    cfg = O.make_cfg("hierarchical", use_vae=False)
+    model, _, _ = _build(cfg, "bf16x3")
+    cmd, arg = O.synth_batch(cfg, 3, seed=4)
+    c, a = cmd.to(DEV), arg.to(DEV)
+    with torch.no_grad():
+        full = model(c, a, c, a, return_tgt=False)
+        vis, zp = model(c, a, None, None, return_hierarch=True)          # (1, Gp, N, 2), (1, Gp, N, dz)
+        assert vis.shape == (1, 8, 3, 2) and zp.shape == (1, 8, 3, cfg.dim_z)
+        again = model(None, None, None, None, z=zp.permute(2, 1, 0, 3), hierarch_logits=vis, return_tgt=False)
+    for k in ("command_logits", "args_logits", "visibility_logits"):
+        assert torch.allclose(again[k], full[k], rtol=1e-5, atol=1e-6), k
