@@ -455,15 +455,30 @@ struct GAttn {
   static constexpr int kSmemBwd = 4 * kTileH * 2 + 2 * kTileP * 2 + LP;
 };
 
+// 16-byte asynchronous global -> shared copy (LDGSTS); !valid zero-fills the destination without reading the source
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Stage one [L x HD] head slice into a zero-padded [LP x HD] tile.  All of a thread's 16-byte pieces are issued as
+// asynchronous copies before anything waits: with a load -> store loop every thread had ONE 16-byte load in flight
+// (15 KB per SM), which capped the first version of this kernel at 1.35 TB/s.
 template <int HD, int NT>
 __device__ __forceinline__ void g_stage(bf16* dst, const bf16* src, int ld, int L) {
   using G = GAttn<HD, NT>;
   constexpr int kParts = HD / 8;
-  for (int chunk = threadIdx.x; chunk < G::LP * kParts; chunk += G::kThreads) {
-    const int row = chunk / kParts, part = chunk % kParts;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (row < L) v = *reinterpret_cast<const uint4*>(src + size_t(row) * ld + part * 8);
-    *reinterpret_cast<uint4*>(dst + row * G::SH + part * 8) = v;
+  const uint32_t d0 = smem_addr(dst);
+#pragma unroll
+  for (int it = 0; it < (G::LP * kParts + G::kThreads - 1) / G::kThreads; ++it) {
+    const int chunk = threadIdx.x + it * G::kThreads;
+    if (chunk < G::LP * kParts) {
+      const int row = chunk / kParts, part = chunk % kParts;
+      const bool ok = row < L;
+      cp_async16(d0 + (row * G::SH + part * 8) * 2, src + (ok ? size_t(row) * ld + part * 8 : 0), ok);
+    }
   }
 }
 
@@ -649,7 +664,9 @@ __global__ void __launch_bounds__(32 * NT) attn_gmma_fwd_kernel(MmaAttnArgs a) {
     g_stage<HD, NT>(Qs, base, ld, L);
     g_stage<HD, NT>(Ks, base + d, ld, L);
     g_stage<HD, NT>(Vs, base + 2 * d, ld, L);
+    cp_async_commit();
     for (int j = threadIdx.x; j < G::LP; j += G::kThreads) kv[j] = (j < L && (a.valid == nullptr || a.valid[row0 + j] != 0)) ? 1 : 0;
+    cp_async_wait_all();
     __syncthreads();
     float s[2 * NT][4];
     g_scores<HD, NT>(s, q_t, k_t, w, lane);
@@ -696,7 +713,9 @@ __global__ void __launch_bounds__(32 * NT) attn_gmma_bwd_kernel(MmaAttnArgs a) {
     g_stage<HD, NT>(Ks, base + d, ld, L);
     g_stage<HD, NT>(Vs, base + 2 * d, ld, L);
     g_stage<HD, NT>(Gs, a.dout + row0 * d + h * HD, d, L);
+    cp_async_commit();
     for (int j = threadIdx.x; j < G::LP; j += G::kThreads) kv[j] = (j < L && (a.valid == nullptr || a.valid[row0 + j] != 0)) ? 1 : 0;
+    cp_async_wait_all();
     __syncthreads();
     float p[2 * NT][4], dp[2 * NT][4];
     g_scores<HD, NT>(p, q_t, k_t, w, lane);
