@@ -99,23 +99,17 @@ def peaks():
 
 
 def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel family, averaged over the launches of
-    the committed `ncu --set full` capture (profiles/r*_ncu_linear.txt, written by tools/summarize_profiles.py)."""
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel family: launch-count-weighted mean over
+    the family's epilogue roles, each captured once with `ncu --set full` at the path-level shape
+    (profiles/r*_linear_modes.json, written by tools/summarize_profiles.py from tools/gpu_artifacts.sh's captures)."""
     try:
         import glob
-        files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_linear.txt")))
-        tot, n = 0.0, 0
-        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        for line in open(files[-1]):
-            if not line.startswith("{"):
-                continue
-            d = json.loads(line)
-            b = 0.0
-            for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                v, u = d[k].split()
-                b += float(v) * unit[u]
-            tot, n = tot + b, n + 1
-        return (tot / n, "%s: mean over %d captured linear_kernel launches" % (os.path.basename(files[-1]), n)) if n else (None, None)
+        files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_linear_modes.json")))
+        modes = json.load(open(files[-1]))
+        n = sum(m["launches_per_step"] for m in modes.values())
+        tot = sum(m["launches_per_step"] * m["dram_bytes"] for m in modes.values())
+        return (tot / n, "%s: launch-weighted mean over %d epilogue roles (%d path-level launches per step)" % (
+            os.path.basename(files[-1]), len(modes), n)) if n else (None, None)
     except Exception:
         return None, None
 

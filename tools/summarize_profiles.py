@@ -57,30 +57,61 @@ def ncu_raw(rep):
     return res
 
 
+MODES = {"qkv": (2, "QKV projection"), "ffn1": (3, "FFN first linear (ReLU + dropout)"),
+         "proj": (4, "out-proj / FFN2 into the fp32 residual stream"), "lnfwd": (8, "mode 4 + fused LayerNorm"),
+         "mask": (5, "dgrad through the ReLU/dropout mask"), "dgrad": (1, "plain dgrad"),
+         "head_dgrad": (6, "args-head dgrad, fp32 accumulate"), "logits": (7, "2827-wide fp32 logits")}
+UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+
+def to_bytes(s):
+    v, u = s.split()
+    return float(v) * UNIT[u]
+
+
 def main():
     g = "gpurun_out/%s_" % R
-    lines = []
+    for src, dst in (("bench_n1", "bench_n1"), ("bench_reference", "bench_reference"), ("bench_fonts", "bench_fonts"),
+                     ("bench_scaled", "bench_scaled"), ("bench_n2", "bench_n2")):
+        if os.path.exists(g + src + ".json") and os.path.getsize(g + src + ".json") > 10:
+            json.dump(json.load(open(g + src + ".json")), open("%s/%s_%s.json" % (OUT, R, dst), "w"), indent=1)
+    if os.path.exists(g + "pytest_gpu.txt"):
+        open("%s/%s_pytest_gpu.txt" % (OUT, R), "w").write(open(g + "pytest_gpu.txt").read())
     bench = json.load(open(g + "bench_n1.json"))
-    ref = json.load(open(g + "bench_reference.json"))
-    json.dump(bench, open("%s/%s_bench_n1.json" % (OUT, R), "w"), indent=1)
-    json.dump(ref, open("%s/%s_bench_reference.json" % (OUT, R), "w"), indent=1)
     n_per_step = int(round(bench["gpu_launches"])) + 25        # + torch fills / copies in the same step
     data, agg = launches(g + "launches.csv", n_per_step)
     tot = sum(a[1] for a in agg.values())
     with open("%s/%s_launch_shares.txt" % (OUT, R), "w") as f:
-        f.write("# one train step (N=512) under `ncu --metrics gpu__time_duration.sum --clock-control none`: last %d launches\n"
-                "# (cold-cache, serialised: compare SHARES, not absolutes).  total %.0f us\n" % (len(data), tot))
+        f.write("# one train step (N=512, eager launches) under `ncu --metrics gpu__time_duration.sum --clock-control none`: last "
+                "%d launches\n# (cold-cache, serialised: compare SHARES, not absolutes).  total %.0f us\n" % (len(data), tot))
         for k, a in sorted(agg.items(), key=lambda x: -x[1][1]):
             f.write("%9.0f us %5.1f%% %4d  %s\n" % (a[1], 100 * a[1] / tot, a[0], k))
-    for name in ("linear", "outer", "attn", "ln_bwd"):
-        rep = g + "prof_%s.ncu-rep" % name
+    # per-role full-set captures of the GEMM family + launches per step of each role -> time-weighted family traffic
+    per_mode = {}
+    with open("%s/%s_ncu_linear.txt" % (OUT, R), "w") as f:
+        f.write("# ncu --set full --clock-control none --import-source on: one launch of every lean epilogue role of "
+                "dsvg::linear_kernel at the path-level shape (tools/prof_mode.py), selected raw metrics\n")
+        for name, (mode, what) in MODES.items():
+            rep = g + "mode_%s.ncu-rep" % name
+            if not os.path.exists(rep):
+                continue
+            for d in ncu_raw(rep)[:1]:
+                d["role"], d["mode"] = what, mode
+                f.write(json.dumps(d) + "\n")
+                n_l = sum(a[0] for k, a in agg.items() if "linear_kernel<256, 1, %d>" % mode in k)
+                per_mode[name] = {"mode": mode, "launches_per_step": n_l,
+                                  "dram_bytes": to_bytes(d["dram__bytes_read.sum"]) + to_bytes(d["dram__bytes_write.sum"]),
+                                  "us": float(d["gpu__time_duration.sum"].split()[0])}
+    json.dump(per_mode, open("%s/%s_linear_modes.json" % (OUT, R), "w"), indent=1)
+    for name in ("outer", "attn", "ln_bwd"):
+        rep = g + "mode_%s.ncu-rep" % name
         if not os.path.exists(rep):
             continue
         with open("%s/%s_ncu_%s.txt" % (OUT, R, name), "w") as f:
             f.write("# ncu --set full --clock-control none, selected raw metrics per captured launch (%s)\n" % rep)
             for d in ncu_raw(rep):
                 f.write(json.dumps(d) + "\n")
-    print("wrote", sorted(os.listdir(OUT)))
+    print("wrote", sorted(x for x in os.listdir(OUT) if x.startswith(R)))
 
 
 if __name__ == "__main__":
