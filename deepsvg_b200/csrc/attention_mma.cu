@@ -9,6 +9,8 @@
 //
 // Dropout on the probabilities uses its own element numbering (8 consecutive draws per (row, lane-in-quad)),
 // identical in forward and backward of THIS kernel.
+#include <cstdlib>
+
 #include "../../include/dsvg_b200.h"
 #include "common.cuh"
 
@@ -386,13 +388,28 @@ __global__ void __launch_bounds__(kMmaWarps * 32) attn_mma_bwd_kernel(MmaAttnArg
 }  // namespace dsvg
 using namespace dsvg;
 
+// Grid cap of the 32 x 32 kernels: 32 CTAs per SM (round-1 tuning), or -- DSVG_ATTN_GRID=occ, development A/B -- exactly one
+// wave of resident CTAs.
+static long long mma_grid_cap(bool bwd) {
+  static const bool occ = [] { const char* e = getenv("DSVG_ATTN_GRID"); return e && e[0] == 'o'; }();
+  if (!occ) return 148LL * 32;
+  static long long cap[2] = {0, 0};
+  if (cap[bwd] == 0) {
+    int n = 0;
+    if (bwd) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, dsvg::attn_mma_bwd_kernel, dsvg::kMmaWarps * 32, size_t(dsvg::kMmaWarps * 6 * dsvg::kTile * 2));
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, dsvg::attn_mma_fwd_kernel, dsvg::kMmaWarps * 32, 0);
+    cap[bwd] = 148LL * (n > 0 ? n : 8);
+  }
+  return cap[bwd];
+}
+
 // Entry points used by attention.cu's dispatcher (not part of the public header: same ABI functions, faster path).
 int dsvg_attn_mma_fwd(const bf16* qkv, const uint8_t* valid, bf16* out, int nseq, int L, int H, Dropout drop,
                       cudaStream_t st) {
   MmaAttnArgs a{};
   a.qkv = qkv; a.valid = valid; a.out = out; a.nseq = nseq; a.L = L; a.H = H; a.scale = 1.f; a.drop = drop;
   long long blocks = ((long long)nseq * H + kMmaWarps - 1) / kMmaWarps;
-  if (blocks > 148LL * 32) blocks = 148LL * 32;
+  if (blocks > mma_grid_cap(false)) blocks = mma_grid_cap(false);
   DSVG_CUDA(launch_k(attn_mma_fwd_kernel, dim3(int(blocks)), dim3(kMmaWarps * 32), 0, st, a));
   ++g_launches;
   return 0;
@@ -402,14 +419,14 @@ int dsvg_attn_mma_bwd(const bf16* qkv, const uint8_t* valid, const bf16* dout, b
   MmaAttnArgs a{};
   a.qkv = qkv; a.valid = valid; a.dout = dout; a.dqkv = dqkv; a.nseq = nseq; a.L = L; a.H = H; a.scale = q_scale;
   a.drop = drop;
-  long long blocks = ((long long)nseq * H + kMmaWarps - 1) / kMmaWarps;
-  if (blocks > 148LL * 32) blocks = 148LL * 32;
   constexpr int smem = kMmaWarps * 6 * kTile * 2;
   static bool configured = false;
   if (!configured) {
     DSVG_CUDA(cudaFuncSetAttribute(attn_mma_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
+  long long blocks = ((long long)nseq * H + kMmaWarps - 1) / kMmaWarps;
+  if (blocks > mma_grid_cap(true)) blocks = mma_grid_cap(true);
   DSVG_CUDA(launch_k(attn_mma_bwd_kernel, dim3(int(blocks)), dim3(kMmaWarps * 32), size_t(smem), st, a));
   ++g_launches;
   return 0;
@@ -642,7 +659,8 @@ __device__ __forceinline__ void g_store_rows_smem(bf16* tile, int st, int row0, 
   }
 }
 
-template <int HD, int NT>
+// DB: two sets of Q/K/V tiles -- the next pair's asynchronous copies fly while the current pair is computed
+template <int HD, int NT, bool DB>
 __global__ void __launch_bounds__(32 * NT) attn_gmma_fwd_kernel(MmaAttnArgs a) {
   using G = GAttn<HD, NT>;
   pdl_launch_dependents();
@@ -651,26 +669,39 @@ __global__ void __launch_bounds__(32 * NT) attn_gmma_fwd_kernel(MmaAttnArgs a) {
   extern __shared__ __align__(16) bf16 sm_dyn[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int L = a.L, d = a.H * HD, ld = 3 * d;
-  bf16* Qs = sm_dyn;
-  bf16* Ks = Qs + G::kTileH;
-  bf16* Vs = Ks + G::kTileH;
-  uint8_t* kv = reinterpret_cast<uint8_t*>(Vs + G::kTileH);
-  const uint32_t q_t = smem_addr(Qs), k_t = smem_addr(Ks), v_t = smem_addr(Vs);
+  constexpr int kSet = 3 * G::kTileH;                       // elements of one Q/K/V set
+  uint8_t* kv_base = reinterpret_cast<uint8_t*>(sm_dyn + (DB ? 2 : 1) * kSet);
   const long long npairs = (long long)a.nseq * a.H;
-  for (long long pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+  auto issue = [&](long long pair, int b) {
     const int seq = int(pair / a.H), h = int(pair % a.H);
     const size_t row0 = size_t(seq) * L;
     const bf16* base = a.qkv + row0 * ld + h * HD;
+    bf16* Qs = sm_dyn + b * kSet;
     g_stage<HD, NT>(Qs, base, ld, L);
-    g_stage<HD, NT>(Ks, base + d, ld, L);
-    g_stage<HD, NT>(Vs, base + 2 * d, ld, L);
+    g_stage<HD, NT>(Qs + G::kTileH, base + d, ld, L);
+    g_stage<HD, NT>(Qs + 2 * G::kTileH, base + 2 * d, ld, L);
     cp_async_commit();
+    uint8_t* kv = kv_base + b * G::LP;
     for (int j = threadIdx.x; j < G::LP; j += G::kThreads) kv[j] = (j < L && (a.valid == nullptr || a.valid[row0 + j] != 0)) ? 1 : 0;
-    cp_async_wait_all();
+  };
+  long long pair = blockIdx.x;
+  int b = 0;
+  if (pair < npairs) issue(pair, 0);
+  for (; pair < npairs; pair += gridDim.x) {
+    const long long next = pair + gridDim.x;
+    if (DB && next < npairs) {
+      issue(next, b ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");   // everything but the group just committed has landed
+    } else {
+      cp_async_wait_all();
+    }
     __syncthreads();
+    const int seq = int(pair / a.H), h = int(pair % a.H);
+    const size_t row0 = size_t(seq) * L;
+    const uint32_t q_t = smem_addr(sm_dyn + b * kSet), k_t = q_t + G::kTileH * 2, v_t = k_t + G::kTileH * 2;
     float s[2 * NT][4];
     g_scores<HD, NT>(s, q_t, k_t, w, lane);
-    g_softmax<NT>(s, g_my_keys<NT>(kv, t));
+    g_softmax<NT>(s, g_my_keys<NT>(kv_base + b * G::LP, t));
     if (a.drop.p > 0.f) {
       float mult[2 * NT][4];
       g_dropout<NT>(mult, a.drop, (unsigned long long)pair, w, g, t);
@@ -682,7 +713,9 @@ __global__ void __launch_bounds__(32 * NT) attn_gmma_fwd_kernel(MmaAttnArgs a) {
     float o[HD / 8][4];
     g_mul_regs<HD, NT>(o, s, v_t, lane);
     g_store_global<HD>(a.out + row0 * d + h * HD, d, L, 16 * w, o, 1.f, g, t);
-    __syncthreads();
+    __syncthreads();                                          // all warps are done with this set before it is refilled
+    if (DB) b ^= 1;
+    else if (next < npairs) issue(next, 0);
   }
 }
 
@@ -763,27 +796,48 @@ __global__ void __launch_bounds__(32 * NT) attn_gmma_bwd_kernel(MmaAttnArgs a) {
   }
 }
 
-template <int HD, int NT>
-static int launch_gmma(bool bwd, const MmaAttnArgs& a, cudaStream_t st) {
+static bool gmma_double_buffer() {
+  static const bool on = [] { const char* e = getenv("DSVG_GMMA_DB"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
+template <int HD, int NT, bool BWD, bool DB>
+static int launch_gmma_k(const MmaAttnArgs& a, cudaStream_t st) {
   using G = GAttn<HD, NT>;
-  const int smem = bwd ? G::kSmemBwd : G::kSmemFwd;
-  static bool configured[2] = {false, false};
-  if (!configured[bwd ? 1 : 0]) {
-    if (bwd) DSVG_CUDA(cudaFuncSetAttribute(attn_gmma_bwd_kernel<HD, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    else DSVG_CUDA(cudaFuncSetAttribute(attn_gmma_fwd_kernel<HD, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured[bwd ? 1 : 0] = true;
+  const int smem = BWD ? G::kSmemBwd : (DB ? 2 : 1) * G::kSmemFwd;
+  auto kern = [] {
+    if constexpr (BWD) return attn_gmma_bwd_kernel<HD, NT>;
+    else return attn_gmma_fwd_kernel<HD, NT, DB>;
+  }();
+  // one wave of resident CTAs (registers AND shared memory decide how many fit: a grid sized from shared memory alone ran a
+  // ragged second wave at half occupancy); the kernel strides over the pairs
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    DSVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int n = 0;
+    DSVG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, G::kThreads, size_t(smem)));
+    per_sm = n > 0 ? n : 1;
+  }
+  int sms = 148;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
   }
   const long long npairs = (long long)a.nseq * a.H;
-  int per_sm = (220 * 1024) / (smem + 1024);
-  if (per_sm > 2048 / G::kThreads) per_sm = 2048 / G::kThreads;
-  if (per_sm > 32) per_sm = 32;
-  if (per_sm < 1) per_sm = 1;
-  long long blocks = 148LL * per_sm;
+  long long blocks = (long long)sms * per_sm;
   if (blocks > npairs) blocks = npairs;
-  if (bwd) DSVG_CUDA(launch_k(attn_gmma_bwd_kernel<HD, NT>, dim3(int(blocks)), dim3(G::kThreads), size_t(smem), st, a));
-  else DSVG_CUDA(launch_k(attn_gmma_fwd_kernel<HD, NT>, dim3(int(blocks)), dim3(G::kThreads), size_t(smem), st, a));
+  DSVG_CUDA(launch_k(kern, dim3(int(blocks)), dim3(G::kThreads), size_t(smem), st, a));
   ++g_launches;
   return 0;
+}
+template <int HD, int NT>
+static int launch_gmma(bool bwd, const MmaAttnArgs& a, cudaStream_t st) {
+  if (bwd) return launch_gmma_k<HD, NT, true, false>(a, st);
+  // double-buffered staging when two sets leave room for >= 2 CTAs per SM
+  if (gmma_double_buffer() && 2 * GAttn<HD, NT>::kSmemFwd <= 100 * 1024) return launch_gmma_k<HD, NT, false, true>(a, st);
+  return launch_gmma_k<HD, NT, false, false>(a, st);
 }
 template <int HD>
 static int launch_gmma_nt(bool bwd, const MmaAttnArgs& a, cudaStream_t st) {

@@ -91,8 +91,12 @@ def test_reference_trainer_call_sequence(variant):
     assert not missing and not unexpected
     with torch.no_grad():
         kw = {"label": labels} if cfg.label_condition else {}
-        torch.manual_seed(5)                      # the VAE samples in eval mode too (model.py:182-187)
+        if cfg.use_vae:                            # the VAE samples in eval mode too (model.py:182-187): inject the noise
+            inner._eps_override = fresh._eps_override = torch.randn(margs[0].shape[0], cfg.dim_z, device=DEV)
         a = inner(margs[0], margs[1], margs[2], margs[3], **kw)["command_logits"]
-        torch.manual_seed(5)
         b = fresh(margs[0], margs[1], margs[2], margs[3], **kw)["command_logits"]
+        # the trained model's cached bf16 weight operands must be casts of its CURRENT fp32 masters
+        stale = [n for (n, _d), (_k, w, _wt) in inner._wcache.items()
+                 if not torch.equal(w.t[0, :, :w.cols].float(), inner._param(n).detach().to(torch.bfloat16).float())]
+        assert not stale, stale
     assert torch.equal(a, b)
