@@ -13,7 +13,7 @@ U64 = C.c_uint64
 DROP = [F, U32, U64]
 
 #: must equal dsvg_abi_version() of the loaded library (checked in _lib.load())
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 SIGNATURES = {
     "dsvg_abi_version": (I, []),
@@ -47,8 +47,8 @@ SIGNATURES = {
     "dsvg_cast_act": (I, [P, I, I, I, P, Z, I, P, Z, I, P, Z, I, F] + DROP + [P]),
     "dsvg_colsum": (I, [P, Z, I, I, I, P, P, P]),
     "dsvg_seg_sum": (I, [P, I, I, I, P, Z, P] + DROP + [P]),
-    "dsvg_gather_rows": (I, [P, P, I, I, P, Z, P]),
-    "dsvg_scatter_rows": (I, [P, P, I, I, P, P]),
+    "dsvg_gather_rows": (I, [P, P, I, I, I, P, Z, P]),
+    "dsvg_scatter_rows": (I, [P, P, I, I, I, P, P]),
     "dsvg_add_f32": (I, [P, P, P, Z, P]),
     "dsvg_grad_sqnorm": (I, [P, I, I, P, P]),
     "dsvg_adamw_step": (I, [P, I, I, F, F, F, F, F, F, F, F, P, P]),

@@ -71,15 +71,25 @@ seg_sum_kernel(const float* __restrict__ in, int nseq, int L, int d, bf16* __res
 }
 
 // label embedding: out[n] = table[label[n]] (act, and fp32 copy unused) ; backward: dtable[label[n]] += g[n]
+// An id outside [0, n_rows) traps (the launch fails) -- nn.Embedding's device-side assert, not a silent read of
+// someone else's memory.
+__device__ __forceinline__ long long checked_row(const long long* idx, int i, int n_rows) {
+  const long long r = idx[i];
+  if (r < 0 || r >= n_rows) {
+    printf("dsvg: label id %lld at position %d is outside the embedding table (%d rows)\n", r, i, n_rows);
+    __trap();
+  }
+  return r;
+}
 __global__ void gather_rows_kernel(const float* __restrict__ table, const long long* __restrict__ idx, int n, int w,
-                                   bf16* __restrict__ out, size_t out_lo) {
+                                   int n_rows, bf16* __restrict__ out, size_t out_lo) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n * w; i += gridDim.x * blockDim.x)
-    act_store(out, out_lo, i, table[size_t(idx[i / w]) * w + (i % w)]);
+    act_store(out, out_lo, i, table[size_t(checked_row(idx, i / w, n_rows)) * w + (i % w)]);
 }
 __global__ void scatter_rows_kernel(const float* __restrict__ g, const long long* __restrict__ idx, int n, int w,
-                                    float* __restrict__ dtable) {
+                                    int n_rows, float* __restrict__ dtable) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n * w; i += gridDim.x * blockDim.x)
-    atomicAdd(dtable + size_t(idx[i / w]) * w + (i % w), g[i]);
+    atomicAdd(dtable + size_t(checked_row(idx, i / w, n_rows)) * w + (i % w), g[i]);
 }
 
 // y = a + b (fp32), used to merge gradient streams of the tiny latent path
@@ -139,21 +149,21 @@ extern "C" int dsvg_seg_sum(const float* in, int nseq, int L, int d, dsvg_bf16* 
   return 0;
 }
 
-extern "C" int dsvg_gather_rows(const float* table, const long long* idx, int n, int w, dsvg_bf16* out,
+extern "C" int dsvg_gather_rows(const float* table, const long long* idx, int n, int w, int n_rows, dsvg_bf16* out,
                                 size_t out_lo_off, void* stream) {
-  DSVG_CHECK(table && idx && out && n > 0 && w > 0, "dsvg_gather_rows: bad arguments");
+  DSVG_CHECK(table && idx && out && n > 0 && w > 0 && n_rows > 0, "dsvg_gather_rows: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  gather_rows_kernel<<<ceil_div((long long)n * w, 256), 256, 0, st>>>(table, idx, n, w, reinterpret_cast<bf16*>(out),
+  gather_rows_kernel<<<ceil_div((long long)n * w, 256), 256, 0, st>>>(table, idx, n, w, n_rows, reinterpret_cast<bf16*>(out),
                                                                      out_lo_off);
   ++g_launches;
   DSVG_LAUNCH_CHECK();
   return 0;
 }
 
-extern "C" int dsvg_scatter_rows(const float* g, const long long* idx, int n, int w, float* dtable, void* stream) {
-  DSVG_CHECK(g && idx && dtable && n > 0 && w > 0, "dsvg_scatter_rows: bad arguments");
+extern "C" int dsvg_scatter_rows(const float* g, const long long* idx, int n, int w, int n_rows, float* dtable, void* stream) {
+  DSVG_CHECK(g && idx && dtable && n > 0 && w > 0 && n_rows > 0, "dsvg_scatter_rows: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  scatter_rows_kernel<<<ceil_div((long long)n * w, 256), 256, 0, st>>>(g, idx, n, w, dtable);
+  scatter_rows_kernel<<<ceil_div((long long)n * w, 256), 256, 0, st>>>(g, idx, n, w, n_rows, dtable);
   ++g_launches;
   DSVG_LAUNCH_CHECK();
   return 0;

@@ -278,12 +278,12 @@ def seg_sum(x, nseq, L, d, *, out=None, out_f32=None, drop=(0.0, 0, 0)):
 
 
 def gather_rows(table, idx, n, w, out):
-    rc = _lib.load().dsvg_gather_rows(table.data_ptr(), idx.data_ptr(), n, w, out.ptr, out.lo, _stream())
+    rc = _lib.load().dsvg_gather_rows(table.data_ptr(), idx.data_ptr(), n, w, table.shape[0], out.ptr, out.lo, _stream())
     _lib.check(rc, "dsvg_gather_rows")
 
 
 def scatter_rows(g, idx, n, w, dtable):
-    rc = _lib.load().dsvg_scatter_rows(g.data_ptr(), idx.data_ptr(), n, w, dtable.data_ptr(), _stream())
+    rc = _lib.load().dsvg_scatter_rows(g.data_ptr(), idx.data_ptr(), n, w, dtable.shape[0], dtable.data_ptr(), _stream())
     _lib.check(rc, "dsvg_scatter_rows")
 
 

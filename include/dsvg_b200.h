@@ -211,10 +211,11 @@ int dsvg_colsum(const dsvg_bf16* a, size_t lo_off, int ld, int M, int N, const f
 /* out[q] = dropout(sum_{s<L} in[q*L+s])  (backward of the linear_global broadcast, improved_transformer.py:131-136) */
 int dsvg_seg_sum(const float* in, int nseq, int L, int d, dsvg_bf16* out, size_t out_lo_off, float* out_f32,
                  float drop_p, uint32_t drop_site, uint64_t seed, void* stream);
-/* LabelEmbedding (model.py:87-89) gather and its gradient scatter-add */
-int dsvg_gather_rows(const float* table, const long long* idx, int n, int w, dsvg_bf16* out, size_t out_lo_off,
+/* LabelEmbedding (model.py:87-89) gather and its gradient scatter-add; table / dtable have n_rows rows of w floats.  An id
+ * outside [0, n_rows) traps on the device (the launch fails), like nn.Embedding's device-side assert. */
+int dsvg_gather_rows(const float* table, const long long* idx, int n, int w, int n_rows, dsvg_bf16* out, size_t out_lo_off,
                      void* stream);
-int dsvg_scatter_rows(const float* g, const long long* idx, int n, int w, float* dtable, void* stream);
+int dsvg_scatter_rows(const float* g, const long long* idx, int n, int w, int n_rows, float* dtable, void* stream);
 int dsvg_add_f32(const float* a, const float* b, float* y, size_t n, void* stream);
 
 /* ---- optimiser step on a table of tensors (config.py:64-65, train.py:99-102) ------------ */

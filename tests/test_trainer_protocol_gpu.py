@@ -53,7 +53,7 @@ def test_reference_trainer_call_sequence(variant):
     loss_fn = SVGLoss(cfg).to(DEV)                                     # default_icons.py:62-63
     optimizer = torch.optim.AdamW(model.parameters(), lr=2e-3)         # deepsvg/config.py:64-65
     sched = torch.optim.lr_scheduler.StepLR(optimizer, step_size=10, gamma=0.9)   # config.py:67-68
-    ds = _Icons(O.make_cfg("hierarchical", **small), 48, cfg.label_condition)
+    ds = _Icons(O.make_cfg("hierarchical", n_labels=cfg.n_labels, **small), 48, cfg.label_condition)
     loader = DataLoader(ds, batch_size=8, shuffle=True, drop_last=True)
     data = next(iter(loader))
     model(*[data[a].to(DEV) for a in model_args], params={})           # train.py:67-72 (single warm-up forward)
