@@ -535,6 +535,8 @@ __device__ __forceinline__ uint32_t g_my_keys(const uint8_t* kv_sm, int t) {
 
 template <int NT>
 __device__ __forceinline__ void g_softmax(float (&s)[2 * NT][4], uint32_t keys) {
+  constexpr uint32_t kAll = (2 * NT * 2 >= 32) ? 0xFFFFFFFFu : ((1u << (2 * NT * 2)) - 1u);
+  const bool masked = (keys & kAll) != kAll;      // warp-uniform per thread quad pattern; unmasked tiles skip the selects
 #pragma unroll
   for (int hrow = 0; hrow < 2; ++hrow) {
     float m = -INFINITY;
@@ -543,7 +545,7 @@ __device__ __forceinline__ void g_softmax(float (&s)[2 * NT][4], uint32_t keys) 
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         float& x = s[nt][2 * hrow + e];
-        if (!((keys >> (2 * nt + e)) & 1u)) x = -INFINITY;
+        if (masked && !((keys >> (2 * nt + e)) & 1u)) x = -INFINITY;
         m = fmaxf(m, x);
       }
     m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
@@ -660,6 +662,9 @@ __device__ __forceinline__ void g_store_rows_smem(bf16* tile, int st, int row0, 
 }
 
 // DB: two sets of Q/K/V tiles -- the next pair's asynchronous copies fly while the current pair is computed
+// ncu (profiles/README.md): the forward is issue/latency-bound, not HBM-bound -- 6.6 k warp instructions per (sequence, head)
+// pair, ALU pipe 45 %, HMMA 24 %, XU 15 %, LSU 47 % at 15 resident warps per SM.  Capping registers for 25 resident warps did
+// not help (417 vs 401 us), so the forward keeps its natural register count and the double-buffered staging.
 template <int HD, int NT, bool DB>
 __global__ void __launch_bounds__(32 * NT) attn_gmma_fwd_kernel(MmaAttnArgs a) {
   using G = GAttn<HD, NT>;
@@ -719,8 +724,10 @@ __global__ void __launch_bounds__(32 * NT) attn_gmma_fwd_kernel(MmaAttnArgs a) {
   }
 }
 
+// backward: 168 registers allowed 2 CTAs per SM; capped at 128 (no spills) for 3: 885 -> 802 us at (4096 x 66, head_dim 64)
+__host__ __device__ constexpr int gmma_bwd_min_ctas(int nt) { return nt >= 5 ? 3 : (nt == 4 ? 4 : 6); }
 template <int HD, int NT>
-__global__ void __launch_bounds__(32 * NT) attn_gmma_bwd_kernel(MmaAttnArgs a) {
+__global__ void __launch_bounds__(32 * NT, gmma_bwd_min_ctas(NT)) attn_gmma_bwd_kernel(MmaAttnArgs a) {
   using G = GAttn<HD, NT>;
   pdl_launch_dependents();
   pdl_wait();
@@ -797,6 +804,7 @@ __global__ void __launch_bounds__(32 * NT) attn_gmma_bwd_kernel(MmaAttnArgs a) {
 }
 
 static bool gmma_double_buffer() {
+  // measured: 401 vs 413 us at (4096 x 66, head_dim 64); DSVG_GMMA_DB=0 switches it off
   static const bool on = [] { const char* e = getenv("DSVG_GMMA_DB"); return !(e && e[0] == '0'); }();
   return on;
 }
