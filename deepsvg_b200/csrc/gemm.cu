@@ -670,7 +670,8 @@ template <int BN, int NPLANES, int MODE>
 __global__ void __launch_bounds__((LinearCfg<BN, NPLANES, MODE>::kThreads), (LinearCfg<BN, NPLANES, MODE>::kCtasPerSm))
 linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
-              const __grid_constant__ CUtensorMap tmC, int M, int N, int K, Epi ep) {
+              const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmM, int M, int N, int K,
+              Epi ep) {
   using Cfg = LinearCfg<BN, NPLANES, MODE>;
   constexpr int kCols = Cfg::kEpiWarps * 8;   // accumulator columns drained per pass of all epilogue warps (64 or 128)
   extern __shared__ uint8_t smem_raw[];
@@ -682,7 +683,8 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   uint64_t* empty_bar = bars + Cfg::kStages;       // [kStages]
   uint64_t* tfull_bar = bars + 2 * Cfg::kStages;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;            // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* mfull_bar = tempty_bar + 2;            // [2] mask boxes of pass 0 / 1 have landed (mode 5)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mfull_bar + 2);
   float* bias_sm = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kStagingBytes + 256);
   float* ln_part = bias_sm + BN;              // modes 8 / 9 only (Cfg::kLnBytes)
   float* ln_acc = ln_part + 2 * 128 * 4 * 2;  // mode 9: [2][256] dgamma / dbeta of this CTA
@@ -702,6 +704,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
+      mbar_init(&mfull_bar[a], 1);
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], Cfg::kEpiWarps);
     }
@@ -853,8 +856,35 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         uint8_t* out_tile = reinterpret_cast<uint8_t*>(staging);
         const int r = quarter * 32 + lane;
         const long long grow = (long long)m0 + r;
+        // Mask dgrad: the ReLU/dropout mask tile arrives by TMA INTO the staging boxes the output is about to overwrite
+        // (same 128-byte swizzle, so a thread finds its row's mask at the very positions it will write).  The per-thread
+        // global loads it replaces read 64 bytes per lane from 32 different rows: latency-bound at 19 % issue / 40 % DRAM.
+        constexpr bool kTmaMask = (FEAT & F_MASK) != 0 && kPasses == 2;
+        constexpr int kBoxesPerPass = kCols / 64;
+        auto issue_mask = [&](int tile_, int pass) {           // storing thread only
+          const int mm0 = (tile_ / n_tiles) * kBlockM, nn0 = (tile_ % n_tiles) * BN;
+          uint32_t bytes = 0;
+#pragma unroll
+          for (int bx = pass * kBoxesPerPass; bx < (pass + 1) * kBoxesPerPass; ++bx)
+            if (nn0 + 64 * bx < N) bytes += kBlockM * 128;
+          mbar_arrive_expect_tx(&mfull_bar[pass], bytes);
+#pragma unroll
+          for (int bx = pass * kBoxesPerPass; bx < (pass + 1) * kBoxesPerPass; ++bx)
+            if (nn0 + 64 * bx < N) tma_load_2d(out_tile + bx * (kBlockM * 128), &tmM, &mfull_bar[pass], nn0 + 64 * bx, mm0);
+        };
+        if constexpr (kTmaMask) {
+          if (warp == 2 && lane == 0) {
+            if (it == 0) {
+              issue_mask(tile, 0);                              // nothing has used the staging tile yet
+              issue_mask(tile, 1);
+            } else {
+              tma_store_wait_read_n<0>();                       // the previous tile's last store has drained its boxes
+              issue_mask(tile, 1);                              // (pass 0 of this tile was requested during the previous tile)
+            }
+          }
+        }
         uint4 mk[2][4];
-        tma_out_load_mask<FEAT>(mk[0], grow, n0 + half * 32, M, N, ep);
+        if constexpr (!kTmaMask) tma_out_load_mask<FEAT>(mk[0], grow, n0 + half * 32, M, N, ep);
         if constexpr (FEAT & F_BIAS) {
           if (n0 != bias_n0) {   // same decision in every epilogue warp (they walk the same tile sequence)
             const int et = threadIdx.x - 64;
@@ -873,7 +903,15 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           if (n0 + c < N) {
             uint32_t v[32];
             tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(acc * BN + c), v);
-            if (ci + 1 < kPasses) tma_out_load_mask<FEAT>(mk[(ci + 1) & 1], grow, n0 + c + kCols, M, N, ep);
+            if constexpr (kTmaMask) {
+              mbar_wait(&mfull_bar[ci], uint32_t(it & 1));
+              const uint8_t* box = out_tile + (c >> 6) * (kBlockM * 128) + r * 128;
+              const int j0 = (c & 63) >> 3;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) mk[ci & 1][q] = *reinterpret_cast<const uint4*>(box + (((j0 + q) ^ (r & 7)) << 4));
+            } else {
+              if (ci + 1 < kPasses) tma_out_load_mask<FEAT>(mk[(ci + 1) & 1], grow, n0 + c + kCols, M, N, ep);
+            }
             tmem_ld_wait();
             tma_out_chunk<FEAT>(v, out_tile, r, grow, n0 + c, c, M, N, ep, mk[ci & 1], smem_u32(bias_sm));
           }
@@ -884,7 +922,14 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);   // TMEM stage drained: the MMA warp may start tile it + 2
           }
           fence_proxy_async_smem();                          // generic-proxy smem writes -> visible to the TMA engine
-          if (warp == 2 && lane == 0) tma_store_wait_read_n<(kPasses - 2)>();   // next pass's boxes are free again
+          if (warp == 2 && lane == 0) {
+            tma_store_wait_read_n<(kPasses - 2)>();   // next pass's boxes are free again
+            if constexpr (kTmaMask) {
+              // pass 0's store of this tile has drained: request the next tile's pass-0 mask into those boxes now, a whole
+              // pass ahead of its use
+              if (ci == 1 && tile + int(gridDim.x) < num_tiles) issue_mask(tile + int(gridDim.x), 0);
+            }
+          }
           named_bar_sync(1, Cfg::kEpiWarps * 32);
           if (warp == 2 && lane == 0) {
 #pragma unroll
@@ -1479,9 +1524,10 @@ static int sm_count() {
 template <int BN, int NPLANES, int MODE>
 static int launch_linear_mode(const CUtensorMap& a, const CUtensorMap& alo, const CUtensorMap& b, const CUtensorMap& blo,
                               int M, int N, int K, const Epi& ep, cudaStream_t st) {
-  CUtensorMap c = a;
+  CUtensorMap c = a, mk = a;
   if (lin_tma_out(MODE)) {
     if (make_map(&c, ep.out_act, N, M, ep.out_act_ld, 64, 128)) return 1;
+    if (ep.mask != nullptr && make_map(&mk, ep.mask, N, M, ep.mask_ld, 64, 128)) return 1;
   }
   using Cfg = LinearCfg<BN, NPLANES, MODE>;
   static bool configured = false;
@@ -1493,8 +1539,8 @@ static int launch_linear_mode(const CUtensorMap& a, const CUtensorMap& alo, cons
   const int tiles = ceil_div(M, kBlockM) * ceil_div(N, BN);
   const int slots = sm_count() * Cfg::kCtasPerSm;
   const int grid = tiles < slots ? tiles : slots;
-  DSVG_CUDA(launch_k(linear_kernel<BN, NPLANES, MODE>, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, st, a, alo, b, blo, c, M,
-                     N, K, ep));
+  DSVG_CUDA(launch_k(linear_kernel<BN, NPLANES, MODE>, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, st, a, alo, b, blo, c, mk,
+                     M, N, K, ep));
   ++g_launches;
   return 0;
 }

@@ -253,7 +253,14 @@ class SVGTransformer(nn.Module):
     def _param(self, name):
         m = self
         for p in name.split("."):
-            m = m._modules[p] if p in m._modules else m._parameters[p]
+            if p in m._modules:
+                m = m._modules[p]
+            elif p in m._parameters:
+                m = m._parameters[p]
+            else:
+                # nn.DataParallel replicas (train.py:74 on several GPUs): replicate() empties `_parameters` and sets the
+                # broadcast copies as plain attributes
+                m = getattr(m, p)
         return m
 
     def _pdict(self):
