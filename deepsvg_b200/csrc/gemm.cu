@@ -636,7 +636,8 @@ __device__ __forceinline__ void tma_out_load_mask(uint4 (&mk)[4], long long grow
 __host__ __device__ constexpr int lin_epi_warps(int mode, int bn) {
   // the fp32-residual epilogues (modes 4, 6) are stall-bound chains of shared / global accesses with no single hot
   // spot (ncu: issue slots 29 % busy with 2 warps per scheduler): the 256-wide, one-CTA-per-SM kernel runs them 16 wide
-  return ((mode >= 3 && mode <= 9) && bn == 256) ? 16 : 8;
+  // mode 6 (head dgrads, K = 2827: 45 k-blocks per tile, a light epilogue): 8 warps leave room for a third operand stage
+  return ((mode >= 3 && mode <= 9 && mode != 6) && bn == 256) ? 16 : 8;
 }
 // act-output lean modes write their bf16 tile through shared memory with one TMA store per 64-column box
 __host__ __device__ constexpr bool lin_tma_out(int mode) { return mode == 1 || mode == 2 || mode == 3 || mode == 5; }
