@@ -36,6 +36,23 @@ def _r8(n):
     return (n + 7) // 8 * 8
 
 
+class _Range:
+    """NVTX range around a phase of the step (DSVG_NVTX=1): `ncu --nvtx --nvtx-include "dsvg/E1.fwd/"` profiles one stack."""
+    on = os.environ.get("DSVG_NVTX", "0") == "1"
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _Range.on:
+            torch.cuda.nvtx.range_push("dsvg/" + self.name)
+
+    def __exit__(self, *a):
+        if _Range.on:
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 # ======================================================================================================
 # parameter inventory (names / shapes / initialisers of the reference module tree, SURVEY.md 8b)
 # ======================================================================================================
@@ -516,14 +533,16 @@ class SVGTransformer(nn.Module):
         nxt = None
         for i in range(n_layers):
             lp = "%s.layers.%d" % (pre, i)
-            rv = self._globals_fwd(sv, lp, zmem, nseq, lab, lab_rpg) if (zmem is not None or lab is not None) else None
+            with _Range(lp + ".fwd.globals"):
+                rv = self._globals_fwd(sv, lp, zmem, nseq, lab, lab_rpg) if (zmem is not None or lab is not None) else None
             rpg = L if zmem is not None else lab_rows_per_group
             if i + 1 < n_layers:
                 nl = "%s.layers.%d" % (pre, i + 1)
                 next_ln = (self._param(nl + ".norm1.weight"), self._param(nl + ".norm1.bias"))
             else:
                 next_ln = (self._param(pre + ".norm.weight"), self._param(pre + ".norm.bias")) if final_ln else None
-            x, nxt = self._layer_fwd(sv, lp, x, M, L, nseq, key_valid, rv, rpg, a_pre=nxt, next_ln=next_ln)
+            with _Range(lp + ".fwd"):
+                x, nxt = self._layer_fwd(sv, lp, x, M, L, nseq, key_valid, rv, rpg, a_pre=nxt, next_ln=next_ln)
         return x, nxt
 
     def _forward_impl(self, inp, seed_dev=None):
@@ -848,7 +867,8 @@ class SVGTransformer(nn.Module):
         for i in reversed(range(n_layers)):
             lp = "%s.layers.%d" % (pre, i)
             prev = self._drop(sv, "%s.layers.%d.drop2" % (pre, i - 1)) if i > 0 else (0.0, 0, 0)
-            dx, dx_act, dx1 = self._layer_bwd(sv, gd, lp, dx, dx_act, M, L, nseq, key_valid, prev, want_dact=i > 0)
+            with _Range(lp + ".bwd"):
+                dx, dx_act, dx1 = self._layer_bwd(sv, gd, lp, dx, dx_act, M, L, nseq, key_valid, prev, want_dact=i > 0)
             if zmem is not None or lab is not None:
                 self._globals_bwd(sv, gd, lp, dx1, nseq, L, zmem, dzmem, lab, dlab, lab_rows_per_group, lab_rpg)
         return dx
