@@ -388,11 +388,9 @@ __global__ void __launch_bounds__(kMmaWarps * 32) attn_mma_bwd_kernel(MmaAttnArg
 }  // namespace dsvg
 using namespace dsvg;
 
-// Grid cap of the 32 x 32 kernels: 32 CTAs per SM (round-1 tuning), or -- DSVG_ATTN_GRID=occ, development A/B -- exactly one
-// wave of resident CTAs.
+// Grid of the 32 x 32 kernels: exactly one wave of resident CTAs (the kernels stride over the pairs); measured against the
+// round-1 cap of 32 CTAs per SM: forward equal (75.2 vs 75.6 us), backward 137.7 vs 142.7 us at (4096 x 32, head_dim 32).
 static long long mma_grid_cap(bool bwd) {
-  static const bool occ = [] { const char* e = getenv("DSVG_ATTN_GRID"); return e && e[0] == 'o'; }();
-  if (!occ) return 148LL * 32;
   static long long cap[2] = {0, 0};
   if (cap[bwd] == 0) {
     int n = 0;
@@ -420,10 +418,9 @@ int dsvg_attn_mma_bwd(const bf16* qkv, const uint8_t* valid, const bf16* dout, b
   a.qkv = qkv; a.valid = valid; a.dout = dout; a.dqkv = dqkv; a.nseq = nseq; a.L = L; a.H = H; a.scale = q_scale;
   a.drop = drop;
   constexpr int smem = kMmaWarps * 6 * kTile * 2;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};
+  if (first_use_on_device(configured)) {
     DSVG_CUDA(cudaFuncSetAttribute(attn_mma_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
   }
   long long blocks = ((long long)nseq * H + kMmaWarps - 1) / kMmaWarps;
   if (blocks > mma_grid_cap(true)) blocks = mma_grid_cap(true);
@@ -820,7 +817,8 @@ static int launch_gmma_k(const MmaAttnArgs& a, cudaStream_t st) {
   // one wave of resident CTAs (registers AND shared memory decide how many fit: a grid sized from shared memory alone ran a
   // ragged second wave at half occupancy); the kernel strides over the pairs
   static int per_sm = 0;
-  if (per_sm == 0) {
+  static bool configured[kMaxDevices] = {};
+  if (first_use_on_device(configured)) {
     DSVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int n = 0;
     DSVG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, G::kThreads, size_t(smem)));

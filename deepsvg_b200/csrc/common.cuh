@@ -193,6 +193,18 @@ __device__ __forceinline__ float warp_max(float v) {
 
 inline int ceil_div(long long a, long long b) { return int((a + b - 1) / b); }
 
+// Function attributes (cudaFuncSetAttribute) are PER DEVICE: a process that drives several GPUs (nn.DataParallel threads)
+// must configure every kernel once on each of them.  `flags` is a function-local static array, one entry per device.
+constexpr int kMaxDevices = 64;
+inline bool first_use_on_device(bool (&flags)[kMaxDevices]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= kMaxDevices) return true;
+  if (flags[dev]) return false;
+  flags[dev] = true;
+  return true;
+}
+
 // ----------------------------------------------------------------------------------------------
 // Programmatic dependent launch.  Kernels launched through launch_k() may start while their predecessor in the stream
 // is still draining: they run their prologue (barrier init, TMEM allocation, descriptor prefetch ...) and then block in

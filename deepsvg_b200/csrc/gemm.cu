@@ -1531,11 +1531,10 @@ static int launch_linear_mode(const CUtensorMap& a, const CUtensorMap& alo, cons
     if (ep.mask != nullptr && make_map(&mk, ep.mask, N, M, ep.mask_ld, 64, 128)) return 1;
   }
   using Cfg = LinearCfg<BN, NPLANES, MODE>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};
+  if (first_use_on_device(configured)) {
     DSVG_CUDA(cudaFuncSetAttribute(linear_kernel<BN, NPLANES, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    Cfg::kSmemBytes));
-    configured = true;
   }
   const int tiles = ceil_div(M, kBlockM) * ceil_div(N, BN);
   const int slots = sm_count() * Cfg::kCtasPerSm;
@@ -1606,11 +1605,10 @@ static int launch_outer(const CUtensorMap& a, const CUtensorMap& alo, const CUte
                         int M, int P, int Q, float alpha, const float* alpha_dev, float* C, int ldc, float* colsum_out,
                         cudaStream_t st) {
   using Cfg = OuterCfg<BQ, NPLANES>;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {};
+  if (first_use_on_device(configured)) {
     DSVG_CUDA(cudaFuncSetAttribute(outer_kernel<BQ, NPLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    Cfg::kSmemBytes));
-    configured = true;
   }
   const int out_tiles = ceil_div(P, 128) * ceil_div(Q, BQ);
   const int total_mblk = ceil_div(M, 64);

@@ -227,6 +227,7 @@ class SVGTransformer(nn.Module):
         if graphs is None:
             graphs = os.environ.get("DSVG_GRAPHS", "1") != "0"
         self.graphs = bool(graphs)
+        self._aligned = None       # DataParallel replicas: aligned stand-ins of the broadcast parameter views
         self._gs = None            # the one live _GraphState
         self.graph_kernel_launches = 0   # kernels launched through graph replays (the library's own counter sees captures only)
         self._gs_streak = (None, 0)
@@ -268,6 +269,9 @@ class SVGTransformer(nn.Module):
 
     # -------------------------------------------------------------------------------------------------
     def _param(self, name):
+        al = self.__dict__.get("_aligned")
+        if al is not None:
+            return al[name]
         m = self
         for p in name.split("."):
             if p in m._modules:
@@ -322,7 +326,13 @@ class SVGTransformer(nn.Module):
             if commands_dec is None or args_dec is None:
                 raise ValueError("self_match needs the decoder targets (commands_dec, args_dec)")
             inputs["match_targets"] = (commands_dec.detach().contiguous().float(), args_dec.detach().contiguous().float())
+        self._aligned = None
         plist = [self._param(n) for n in self._pnames]
+        if any(p.data_ptr() % 16 for p in plist):
+            # nn.DataParallel replica: its parameters are views into one coalesced broadcast buffer and only 4-byte aligned;
+            # the kernels read parameters with 16-byte vector loads.  Differentiable aligned copies stand in for them.
+            plist = [p if p.data_ptr() % 16 == 0 else p.clone() for p in plist]
+            self._aligned = dict(zip(self._pnames, plist))
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in plist)
         token = torch.zeros((), device=ref.device, requires_grad=need_grad)
         need_grad = need_grad and not return_hierarch and hierarch_logits is None   # inference-only exits

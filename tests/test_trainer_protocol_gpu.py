@@ -96,7 +96,8 @@ def test_reference_trainer_call_sequence(variant):
         a = inner(margs[0], margs[1], margs[2], margs[3], **kw)["command_logits"]
         b = fresh(margs[0], margs[1], margs[2], margs[3], **kw)["command_logits"]
         # the trained model's cached bf16 weight operands must be casts of its CURRENT fp32 masters
-        stale = [n for (n, _d), (_k, w, _wt) in inner._wcache.items()
-                 if not torch.equal(w.t[0, :, :w.cols].float(), inner._param(n).detach().to(torch.bfloat16).float())]
+        stale = [n for (n, d_), (_k, w, _wt) in inner._wcache.items()      # (entries of other devices belong to DP replicas)
+                 if d_ == inner._param(n).device
+                 and not torch.equal(w.t[0, :, :w.cols].float(), inner._param(n).detach().to(torch.bfloat16).float())]
         assert not stale, stale
     assert torch.equal(a, b)
