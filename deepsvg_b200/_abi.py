@@ -13,7 +13,7 @@ U64 = C.c_uint64
 DROP = [F, U32, U64]
 
 #: must equal dsvg_abi_version() of the loaded library (checked in _lib.load())
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 SIGNATURES = {
     "dsvg_abi_version": (I, []),
@@ -35,8 +35,8 @@ SIGNATURES = {
     "dsvg_ln_fwd": (I, [P, P, P, P, Z, P, P, I, I, P]),
     "dsvg_ln_pool_fwd": (I, [P, P, P, P, P, P, P, P, I, I, I, P]),
     "dsvg_ln_bwd": (I, [P, P, P, P, P, Z, P, P, P, I, P, P, P, Z] + DROP + [P, P, I, I, P]),
-    "dsvg_attn_fwd": (I, [P, Z, P, P, Z, I, I, I, I] + DROP + [P]),
-    "dsvg_attn_bwd": (I, [P, Z, P, P, Z, P, Z, I, I, I, I, F] + DROP + [P]),
+    "dsvg_attn_fwd": (I, [P, Z, P, P, Z, I, I, I, I, I] + DROP + [P]),
+    "dsvg_attn_bwd": (I, [P, Z, P, P, Z, P, Z, I, I, I, I, I, F] + DROP + [P]),
     "dsvg_ce_args": (I, [P, I, P, P, P, P, Z, I, P, I, I, I, I, P]),
     "dsvg_ce_cmd": (I, [P, P, P, P, P, P, Z, I, P, I, I, I, P]),
     "dsvg_ce_vis": (I, [P, P, P, Z, I, P, I, F, P]),

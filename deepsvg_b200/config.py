@@ -33,7 +33,7 @@ class _DefaultConfig:
         def pair(stages, rel):
             sfx = "_grouped" if stages <= 1 else ""
             return ["commands" + sfx, ("args_rel" if rel else "args") + sfx]
-        fields = pair(self.encode_stages, False) + pair(self.decode_stages, self.rel_targets)
+        fields = pair(self.encode_stages, False) + pair(self.decode_stages, self.rel_targets)   # model/config.py:47-56
         return fields + (["label"] if self.label_condition else [])
 
 
@@ -49,11 +49,11 @@ class HierarchicalSelfMatching(_DefaultConfig):  # model/config.py:101-108
     VARIANT = dict(encode_stages=2, decode_stages=2, self_match=True)
 
 
-class SketchRNN(_DefaultConfig):                # model/config.py:63-71 (rejected by check_supported)
+class SketchRNN(_DefaultConfig):                # model/config.py:63-71 (rejected by check_supported: LSTM)
     VARIANT = dict(model_type="lstm", pred_mode="autoregressive", rel_targets=True)
 
 
-class Sketchformer(_DefaultConfig):             # model/config.py:74-80 (rejected by check_supported)
+class Sketchformer(_DefaultConfig):             # model/config.py:74-80
     VARIANT = dict(pred_mode="autoregressive", rel_targets=True)
 
 
@@ -62,10 +62,11 @@ def check_supported(cfg):
     Everything else raises at construction: there is no slow path to fall back to."""
     if getattr(cfg, "model_type", "transformer") != "transformer":
         raise NotImplementedError("deepsvg_b200: model_type='lstm' is outside the accelerated path")
-    if getattr(cfg, "pred_mode", "one_shot") != "one_shot":
-        raise NotImplementedError("deepsvg_b200: pred_mode='autoregressive' is outside the accelerated path")
-    if getattr(cfg, "rel_targets", False):
-        raise NotImplementedError("deepsvg_b200: rel_targets=True is outside the accelerated path")
+    pm = getattr(cfg, "pred_mode", "one_shot")
+    if pm not in ("one_shot", "autoregressive"):
+        raise NotImplementedError("deepsvg_b200: unknown pred_mode %r" % (pm,))
+    if pm == "autoregressive" and not (cfg.encode_stages == 1 and cfg.decode_stages == 1):
+        raise NotImplementedError("deepsvg_b200: the autoregressive decoder is covered for the one-stage model (Sketchformer)")
     if getattr(cfg, "self_match", False) and not (cfg.encode_stages == 2 and cfg.decode_stages == 2):
         raise NotImplementedError("deepsvg_b200: self_match=True expects the two-stage model (model.py:385)")
     if getattr(cfg, "self_match", False) and (cfg.num_groups_proposal > 16 or cfg.max_num_groups > cfg.num_groups_proposal):
@@ -81,8 +82,8 @@ def check_supported(cfg):
         raise NotImplementedError("deepsvg_b200: dim_feedforward, dim_z, dim_label must be multiples of 8")
     if cfg.n_args != 11 or cfg.n_commands != N_COMMANDS:
         raise NotImplementedError("deepsvg_b200: n_args=11 / n_commands=7 are fixed by the SVG token vocabulary")
-    if cfg.args_dim + 1 > 288:
-        raise NotImplementedError("deepsvg_b200: args_dim must be <= 287")
+    if (2 * cfg.args_dim if getattr(cfg, "rel_targets", False) else cfg.args_dim + 1) > 512:
+        raise NotImplementedError("deepsvg_b200: at most 512 classes per argument slot (args_dim <= 511, or 256 with rel_targets)")
     # sequence lengths the attention kernels hold on chip (csrc/attention.cu: the backward keeps Q, K, V, dO and two
     # L x L tiles of one (sequence, head) pair in shared memory; csrc/attention_mma.cu: L <= 80 on the tensor-core path)
     two = cfg.encode_stages == 2

@@ -29,6 +29,7 @@ struct AttnArgs {
   int nseq, L, H;
   float scale;           // bwd: dq is multiplied by this (the folded q scaling)
   Dropout drop;
+  int causal;            // 1: query i sees keys j <= i only (square_subsequent_mask, model/utils.py:69-72)
 };
 
 template <int HD>
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(AttnArgs a) {
         float m = -INFINITY;
         for (int j = 0; j < L; ++j) {
           float s = dot_smem<HD>(q, Ks + j * HD);
-          if (a.valid != nullptr && !a.valid[row0 + j]) s = -INFINITY;
+          if ((a.valid != nullptr && !a.valid[row0 + j]) || (a.causal && j > i)) s = -INFINITY;
           prow[j] = s;
           m = fmaxf(m, s);
         }
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(AttnArgs a) {
         float m = -INFINITY;
         for (int j = 0; j < L; ++j) {
           float s = dot_smem<HD>(q, Ks + j * HD);
-          if (a.valid != nullptr && !a.valid[row0 + j]) s = -INFINITY;
+          if ((a.valid != nullptr && !a.valid[row0 + j]) || (a.causal && j > i)) s = -INFINITY;
           prow[j] = s;
           m = fmaxf(m, s);
         }
@@ -251,12 +252,12 @@ static int launch_attn(bool bwd, const AttnArgs& a, cudaStream_t st) {
 using namespace dsvg;
 
 // tensor-core (mma.sync) fast path, attention_mma.cu
-int dsvg_attn_mma_fwd(const bf16* qkv, const uint8_t* valid, bf16* out, int nseq, int L, int H, Dropout drop,
+int dsvg_attn_mma_fwd(const bf16* qkv, const uint8_t* valid, bf16* out, int nseq, int L, int H, Dropout drop, int causal,
                       cudaStream_t st);
 int dsvg_attn_mma_bwd(const bf16* qkv, const uint8_t* valid, const bf16* dout, bf16* dqkv, int nseq, int L, int H,
-                      float q_scale, Dropout drop, cudaStream_t st);
+                      float q_scale, Dropout drop, int causal, cudaStream_t st);
 int dsvg_attn_gmma(bool bwd, const bf16* qkv, const uint8_t* valid, bf16* out, const bf16* dout, bf16* dqkv, int nseq, int L,
-                   int H, int head_dim, float q_scale, Dropout drop, cudaStream_t st);
+                   int H, int head_dim, float q_scale, Dropout drop, int causal, cudaStream_t st);
 static bool attn_simt_forced() {
   static const bool off = [] { const char* e = getenv("DSVG_ATTN"); return e && e[0] == 's'; }();  // "simt"
   return off;
@@ -270,19 +271,19 @@ static bool use_gmma(bool single_plane, int L, int head_dim) {
 }
 
 extern "C" int dsvg_attn_fwd(const dsvg_bf16* qkv, size_t qkv_lo_off, const uint8_t* key_valid, dsvg_bf16* out,
-                             size_t out_lo_off, int nseq, int L, int H, int head_dim, float drop_p, uint32_t drop_site,
-                             uint64_t seed, void* stream) {
+                             size_t out_lo_off, int nseq, int L, int H, int head_dim, int causal, float drop_p,
+                             uint32_t drop_site, uint64_t seed, void* stream) {
   DSVG_CHECK(qkv && out && nseq > 0 && L > 0 && H > 0, "dsvg_attn_fwd: bad arguments");
   AttnArgs a{};
   a.qkv = reinterpret_cast<const bf16*>(qkv); a.qkv_lo = qkv_lo_off; a.valid = key_valid;
   a.out = reinterpret_cast<bf16*>(out); a.out_lo = out_lo_off;
-  a.nseq = nseq; a.L = L; a.H = H; a.scale = 1.f;
+  a.nseq = nseq; a.L = L; a.H = H; a.scale = 1.f; a.causal = causal ? 1 : 0;
   a.drop = make_dropout(drop_p, drop_site, seed);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (use_mma(qkv_lo_off == 0 && out_lo_off == 0, L, head_dim))
-    return dsvg_attn_mma_fwd(a.qkv, key_valid, a.out, nseq, L, H, a.drop, st);
+    return dsvg_attn_mma_fwd(a.qkv, key_valid, a.out, nseq, L, H, a.drop, a.causal, st);
   if (use_gmma(qkv_lo_off == 0 && out_lo_off == 0, L, head_dim))
-    return dsvg_attn_gmma(false, a.qkv, key_valid, a.out, nullptr, nullptr, nseq, L, H, head_dim, 1.f, a.drop, st);
+    return dsvg_attn_gmma(false, a.qkv, key_valid, a.out, nullptr, nullptr, nseq, L, H, head_dim, 1.f, a.drop, a.causal, st);
   if (head_dim == 32) return launch_attn<32>(false, a, st);
   if (head_dim == 64) return launch_attn<64>(false, a, st);
   if (head_dim == 16) return launch_attn<16>(false, a, st);
@@ -291,20 +292,20 @@ extern "C" int dsvg_attn_fwd(const dsvg_bf16* qkv, size_t qkv_lo_off, const uint
 
 extern "C" int dsvg_attn_bwd(const dsvg_bf16* qkv, size_t qkv_lo_off, const uint8_t* key_valid, const dsvg_bf16* dout,
                              size_t dout_lo_off, dsvg_bf16* dqkv, size_t dqkv_lo_off, int nseq, int L, int H,
-                             int head_dim, float q_scale, float drop_p, uint32_t drop_site, uint64_t seed,
+                             int head_dim, int causal, float q_scale, float drop_p, uint32_t drop_site, uint64_t seed,
                              void* stream) {
   DSVG_CHECK(qkv && dout && dqkv && nseq > 0 && L > 0 && H > 0, "dsvg_attn_bwd: bad arguments");
   AttnArgs a{};
   a.qkv = reinterpret_cast<const bf16*>(qkv); a.qkv_lo = qkv_lo_off; a.valid = key_valid;
   a.dout = reinterpret_cast<const bf16*>(dout); a.dout_lo = dout_lo_off;
   a.dqkv = reinterpret_cast<bf16*>(dqkv); a.dqkv_lo = dqkv_lo_off;
-  a.nseq = nseq; a.L = L; a.H = H; a.scale = q_scale;
+  a.nseq = nseq; a.L = L; a.H = H; a.scale = q_scale; a.causal = causal ? 1 : 0;
   a.drop = make_dropout(drop_p, drop_site, seed);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (use_mma(qkv_lo_off == 0 && dout_lo_off == 0 && dqkv_lo_off == 0, L, head_dim))
-    return dsvg_attn_mma_bwd(a.qkv, key_valid, a.dout, a.dqkv, nseq, L, H, q_scale, a.drop, st);
+    return dsvg_attn_mma_bwd(a.qkv, key_valid, a.dout, a.dqkv, nseq, L, H, q_scale, a.drop, a.causal, st);
   if (use_gmma(qkv_lo_off == 0 && dout_lo_off == 0 && dqkv_lo_off == 0, L, head_dim))
-    return dsvg_attn_gmma(true, a.qkv, key_valid, nullptr, a.dout, a.dqkv, nseq, L, H, head_dim, q_scale, a.drop, st);
+    return dsvg_attn_gmma(true, a.qkv, key_valid, nullptr, a.dout, a.dqkv, nseq, L, H, head_dim, q_scale, a.drop, a.causal, st);
   if (head_dim == 32) return launch_attn<32>(true, a, st);
   if (head_dim == 64) return launch_attn<64>(true, a, st);
   if (head_dim == 16) return launch_attn<16>(true, a, st);

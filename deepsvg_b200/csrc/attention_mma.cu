@@ -29,6 +29,7 @@ struct MmaAttnArgs {
   int nseq, L, H;
   float scale;
   Dropout drop;
+  int causal;           // query i sees keys j <= i only
 };
 
 __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -87,19 +88,22 @@ __device__ __forceinline__ void stage_tile(bf16* dst, const bf16* src, int ld, i
 }
 
 // scores -> probabilities in the C-fragment layout.  s[mt][nt][e]: row 16*mt + g + 8*(e>>1), col 8*nt + 2*t + (e&1)
-__device__ __forceinline__ void softmax_rows(float (&s)[2][4][4], uint32_t key_mask, int t) {
+__device__ __forceinline__ void softmax_rows(float (&s)[2][4][4], uint32_t key_mask, int t, int g = 0, int causal = 0) {
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
     for (int hrow = 0; hrow < 2; ++hrow) {
       float m = -INFINITY;
+      // causal: row i = 16 mt + g + 8 hrow sees keys j <= i, i.e. the low i + 1 bits of the key mask
+      const int i = 16 * mt + g + 8 * hrow;
+      const uint32_t km = causal ? (key_mask & (0xFFFFFFFFu >> (31 - i))) : key_mask;
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int j = 8 * nt + 2 * t + e;
           float& x = s[mt][nt][2 * hrow + e];
-          if (!((key_mask >> j) & 1u)) x = -INFINITY;
+          if (!((km >> j) & 1u)) x = -INFINITY;
           m = fmaxf(m, x);
         }
       m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
@@ -289,7 +293,7 @@ __global__ void __launch_bounds__(kMmaWarps * 32) attn_mma_fwd_kernel(MmaAttnArg
     __syncwarp();
     float s[2][4][4];
     qk_scores(s, q_t, k_t, lane);
-    softmax_rows(s, kmask, t);
+    softmax_rows(s, kmask, t, g, a.causal);
     if (a.drop.p > 0.f) {
       float mult[2][4][4];
       dropout_tile(mult, a.drop, (unsigned long long)pair, g, t);
@@ -335,7 +339,7 @@ __global__ void __launch_bounds__(kMmaWarps * 32) attn_mma_bwd_kernel(MmaAttnArg
     __syncwarp();
     float p[2][4][4], dp[2][4][4];
     qk_scores(p, q_t, k_t, lane);
-    softmax_rows(p, kmask, t);
+    softmax_rows(p, kmask, t, g, a.causal);
     qk_scores(dp, g_t, v_t, lane);            // dP = dO . V^T  (same operand shapes as Q . K^T)
     if (a.drop.p > 0.f) {
       float mult[2][4][4];
@@ -402,10 +406,11 @@ static long long mma_grid_cap(bool bwd) {
 }
 
 // Entry points used by attention.cu's dispatcher (not part of the public header: same ABI functions, faster path).
-int dsvg_attn_mma_fwd(const bf16* qkv, const uint8_t* valid, bf16* out, int nseq, int L, int H, Dropout drop,
+int dsvg_attn_mma_fwd(const bf16* qkv, const uint8_t* valid, bf16* out, int nseq, int L, int H, Dropout drop, int causal,
                       cudaStream_t st) {
   MmaAttnArgs a{};
   a.qkv = qkv; a.valid = valid; a.out = out; a.nseq = nseq; a.L = L; a.H = H; a.scale = 1.f; a.drop = drop;
+  a.causal = causal;
   long long blocks = ((long long)nseq * H + kMmaWarps - 1) / kMmaWarps;
   if (blocks > mma_grid_cap(false)) blocks = mma_grid_cap(false);
   DSVG_CUDA(launch_k(attn_mma_fwd_kernel, dim3(int(blocks)), dim3(kMmaWarps * 32), 0, st, a));
@@ -413,10 +418,10 @@ int dsvg_attn_mma_fwd(const bf16* qkv, const uint8_t* valid, bf16* out, int nseq
   return 0;
 }
 int dsvg_attn_mma_bwd(const bf16* qkv, const uint8_t* valid, const bf16* dout, bf16* dqkv, int nseq, int L, int H,
-                      float q_scale, Dropout drop, cudaStream_t st) {
+                      float q_scale, Dropout drop, int causal, cudaStream_t st) {
   MmaAttnArgs a{};
   a.qkv = qkv; a.valid = valid; a.dout = dout; a.dqkv = dqkv; a.nseq = nseq; a.L = L; a.H = H; a.scale = q_scale;
-  a.drop = drop;
+  a.drop = drop; a.causal = causal;
   constexpr int smem = kMmaWarps * 6 * kTile * 2;
   static bool configured[kMaxDevices] = {};
   if (first_use_on_device(configured)) {
@@ -530,19 +535,22 @@ __device__ __forceinline__ uint32_t g_my_keys(const uint8_t* kv_sm, int t) {
   return bits;
 }
 
+// row0: first query row of this warp's tile; t: lane & 3; g: lane >> 2; causal: query i sees keys j <= i only
 template <int NT>
-__device__ __forceinline__ void g_softmax(float (&s)[2 * NT][4], uint32_t keys) {
+__device__ __forceinline__ void g_softmax(float (&s)[2 * NT][4], uint32_t keys, int row0 = 0, int g = 0, int t = 0,
+                                          int causal = 0) {
   constexpr uint32_t kAll = (2 * NT * 2 >= 32) ? 0xFFFFFFFFu : ((1u << (2 * NT * 2)) - 1u);
-  const bool masked = (keys & kAll) != kAll;      // warp-uniform per thread quad pattern; unmasked tiles skip the selects
+  const bool masked = causal || (keys & kAll) != kAll;   // unmasked tiles skip the selects
 #pragma unroll
   for (int hrow = 0; hrow < 2; ++hrow) {
     float m = -INFINITY;
+    const int i = row0 + g + 8 * hrow;
 #pragma unroll
     for (int nt = 0; nt < 2 * NT; ++nt)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         float& x = s[nt][2 * hrow + e];
-        if (masked && !((keys >> (2 * nt + e)) & 1u)) x = -INFINITY;
+        if (masked && (!((keys >> (2 * nt + e)) & 1u) || (causal && 8 * nt + 2 * t + e > i))) x = -INFINITY;
         m = fmaxf(m, x);
       }
     m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
@@ -703,7 +711,7 @@ __global__ void __launch_bounds__(32 * NT) attn_gmma_fwd_kernel(MmaAttnArgs a) {
     const uint32_t q_t = smem_addr(sm_dyn + b * kSet), k_t = q_t + G::kTileH * 2, v_t = k_t + G::kTileH * 2;
     float s[2 * NT][4];
     g_scores<HD, NT>(s, q_t, k_t, w, lane);
-    g_softmax<NT>(s, g_my_keys<NT>(kv_base + b * G::LP, t));
+    g_softmax<NT>(s, g_my_keys<NT>(kv_base + b * G::LP, t), 16 * w, g, t, a.causal);
     if (a.drop.p > 0.f) {
       float mult[2 * NT][4];
       g_dropout<NT>(mult, a.drop, (unsigned long long)pair, w, g, t);
@@ -756,7 +764,7 @@ __global__ void __launch_bounds__(32 * NT, gmma_bwd_min_ctas(NT)) attn_gmma_bwd_
     __syncthreads();
     float p[2 * NT][4], dp[2 * NT][4];
     g_scores<HD, NT>(p, q_t, k_t, w, lane);
-    g_softmax<NT>(p, g_my_keys<NT>(kv, t));
+    g_softmax<NT>(p, g_my_keys<NT>(kv, t), 16 * w, g, t, a.causal);
     g_scores<HD, NT>(dp, g_t, v_t, w, lane);          // dP = dO . V^T
     if (a.drop.p > 0.f) {
       float mult[2 * NT][4];
@@ -861,10 +869,10 @@ static int launch_gmma_nt(bool bwd, const MmaAttnArgs& a, cudaStream_t st) {
 
 // head_dim 32 / 64, L <= 80, single-plane operands
 int dsvg_attn_gmma(bool bwd, const bf16* qkv, const uint8_t* valid, bf16* out, const bf16* dout, bf16* dqkv, int nseq, int L,
-                   int H, int head_dim, float q_scale, Dropout drop, cudaStream_t st) {
+                   int H, int head_dim, float q_scale, Dropout drop, int causal, cudaStream_t st) {
   MmaAttnArgs a{};
   a.qkv = qkv; a.valid = valid; a.out = out; a.dout = dout; a.dqkv = dqkv; a.nseq = nseq; a.L = L; a.H = H;
-  a.scale = q_scale; a.drop = drop;
+  a.scale = q_scale; a.drop = drop; a.causal = causal;
   if (head_dim == 32) return launch_gmma_nt<32>(bwd, a, st);
   if (head_dim == 64) return launch_gmma_nt<64>(bwd, a, st);
   DSVG_CHECK(false, "tensor-core attention: head_dim %d unsupported", head_dim);

@@ -419,7 +419,12 @@ extern "C" int dsvg_embed_bwd(const float* commands, const float* args, const ui
   a.spb = 4;
   a.drop = make_dropout(drop_p, drop_site, seed);
   const size_t smem = sizeof(float) * size_t(7 + a.n_grp) * d + sizeof(int) * size_t(a.spb) * L * (3 + n_args);
-  DSVG_CHECK(smem <= 48 * 1024, "dsvg_embed_bwd: sequence too long for the id staging buffer (%zu bytes)", smem);
+  DSVG_CHECK(smem <= 200 * 1024, "dsvg_embed_bwd: sequence too long for the id staging buffer (%zu bytes)", smem);
+  if (smem > 48 * 1024) {     // long one-stage sequences: the group table alone is (max_total_len + 2) x d floats
+    static bool configured[kMaxDevices] = {};
+    if (first_use_on_device(configured))
+      DSVG_CUDA(cudaFuncSetAttribute(embed_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  }
   embed_bwd_kernel<<<ceil_div(nseq, a.spb), d, smem, st>>>(a);
   ++g_launches;
   DSVG_LAUNCH_CHECK();

@@ -1631,7 +1631,7 @@ static int launch_outer(const CUtensorMap& a, const CUtensorMap& alo, const CUte
 using namespace dsvg;
 
 extern "C" const char* dsvg_last_error(void) { return dsvg::last_error(); }
-extern "C" int dsvg_abi_version(void) { return 3; }
+extern "C" int dsvg_abi_version(void) { return 4; }
 extern "C" void dsvg_debug_outer_desc(unsigned lbo, unsigned sbo) {
   dsvg::g_outer_lbo = lbo;
   dsvg::g_outer_sbo = sbo;

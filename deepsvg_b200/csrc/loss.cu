@@ -26,6 +26,7 @@ __constant__ uint8_t c_cmd_args_mask[7][11] = {
 // ---------------------------------------------------------------------------------------------------------
 // argument slots: one warp per target token, 11 slots x C classes
 // ---------------------------------------------------------------------------------------------------------
+template <int KR>   // classes per slot <= 32 * KR
 __global__ void __launch_bounds__(256)
 ce_args_kernel(const float* __restrict__ logits, int ld_logits, const float* __restrict__ commands,
                const float* __restrict__ args, const float* __restrict__ counts, bf16* __restrict__ dl, size_t dl_lo,
@@ -52,10 +53,10 @@ ce_args_kernel(const float* __restrict__ logits, int ld_logits, const float* __r
         continue;
       }
       const int tgt = int(args[src * n_args + k]) + 1;  // shift due to the -1 PAD value (loss.py:54)
-      float v[9];
+      float v[KR];
       float m = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < 9; ++i) {
+      for (int i = 0; i < KR; ++i) {
         const int j = lane + 32 * i;
         v[i] = j < C ? l[j] : -INFINITY;
         m = fmaxf(m, v[i]);
@@ -63,18 +64,18 @@ ce_args_kernel(const float* __restrict__ logits, int ld_logits, const float* __r
       m = warp_max(m);
       float s = 0.f;
 #pragma unroll
-      for (int i = 0; i < 9; ++i) s += (lane + 32 * i < C) ? expf(v[i] - m) : 0.f;
+      for (int i = 0; i < KR; ++i) s += (lane + 32 * i < C) ? expf(v[i] - m) : 0.f;
       s = warp_sum(s);
       const float lse = m + logf(s);
       float lt = 0.f;  // logit of the target class: lane (tgt & 31), register (tgt >> 5); tgt is warp-uniform
 #pragma unroll
-      for (int i = 0; i < 9; ++i) {
+      for (int i = 0; i < KR; ++i) {
         const float cand = __shfl_sync(0xffffffffu, v[i], tgt & 31);
         if (i == (tgt >> 5)) lt = cand;
       }
       if (lane == 0) loss += lse - lt;
 #pragma unroll
-      for (int i = 0; i < 9; ++i) {
+      for (int i = 0; i < KR; ++i) {
         const int j = lane + 32 * i;
         if (j < C) {
           float g = (expf(v[i] - lse) - (j == tgt ? 1.f : 0.f)) * inv_cnt;
@@ -211,12 +212,17 @@ extern "C" int dsvg_ce_args(const float* logits, int ld_logits, const float* com
                             const float* counts, dsvg_bf16* dlogits, size_t dl_lo_off, int ld_dl, float* acc, int nseq,
                             int L, int n_args, int n_classes, void* stream) {
   DSVG_CHECK(logits && commands && args && counts && dlogits && acc, "dsvg_ce_args: null pointer");
-  DSVG_CHECK(n_classes <= 288 && n_args <= 11, "dsvg_ce_args: at most 288 classes x 11 slots");
+  DSVG_CHECK(n_classes <= 512 && n_args <= 11, "dsvg_ce_args: at most 512 classes x 11 slots");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long toks = (long long)nseq * (L - 1);
-  ce_args_kernel<<<ceil_div(toks, 8), 256, 0, st>>>(logits, ld_logits, commands, args, counts,
-                                                    reinterpret_cast<bf16*>(dlogits), dl_lo_off, ld_dl, acc, nseq, L,
-                                                    n_args, n_classes);
+  if (n_classes <= 288)
+    ce_args_kernel<9><<<ceil_div(toks, 8), 256, 0, st>>>(logits, ld_logits, commands, args, counts,
+                                                         reinterpret_cast<bf16*>(dlogits), dl_lo_off, ld_dl, acc, nseq, L,
+                                                         n_args, n_classes);
+  else   // relative-argument targets: 2 * args_dim classes (loss.py:15)
+    ce_args_kernel<16><<<ceil_div(toks, 8), 256, 0, st>>>(logits, ld_logits, commands, args, counts,
+                                                          reinterpret_cast<bf16*>(dlogits), dl_lo_off, ld_dl, acc, nseq, L,
+                                                          n_args, n_classes);
   ++g_launches;
   DSVG_LAUNCH_CHECK();
   return 0;

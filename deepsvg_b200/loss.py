@@ -90,7 +90,7 @@ class SVGLoss(nn.Module):
     def __init__(self, cfg):
         super().__init__()
         self.cfg = cfg
-        self.args_dim = cfg.args_dim + 1
+        self.args_dim = 2 * cfg.args_dim if getattr(cfg, "rel_targets", False) else cfg.args_dim + 1   # loss.py:15
         self.register_buffer("cmd_args_mask", CMD_ARGS_MASK.clone())   # loss.py:17
         self.process_group = None
 

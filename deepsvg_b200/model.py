@@ -122,10 +122,19 @@ def _param_specs(cfg):
         lin("decoder.hierarchical_fcn.visibility_fcn", 2, d)
         lin("decoder.hierarchical_fcn.z_fcn", dz, d)
     dec_len = (cfg.max_seq_len if two else cfg.max_total_len) + 1
-    S.append(("decoder.embedding.PE.pos_embed.weight", (dec_len, d), "kaiming"))
+    out_classes = 2 * cfg.args_dim if getattr(cfg, "rel_targets", False) else cfg.args_dim + 1     # model.py:37,233
+    if getattr(cfg, "pred_mode", "one_shot") == "autoregressive":        # model.py:218-222: SVGEmbedding of the shifted targets
+        S.append(("decoder.embedding.command_embed.weight", (cfg.n_commands, d), "kaiming"))
+        S.append(("decoder.embedding.arg_embed.weight", (out_classes, 64), "kaiming"))
+        S.append(("decoder.embedding.embed_fcn.weight", (d, 64 * cfg.n_args), "kaiming"))
+        S.append(("decoder.embedding.embed_fcn.bias", (d,), "linb:%d" % (64 * cfg.n_args)))
+        S.append(("decoder.embedding.group_embed.weight", (cfg.max_total_len + 2, d), "kaiming"))
+        S.append(("decoder.embedding.pos_encoding.pos_embed.weight", (cfg.max_total_len + 2, d), "kaiming"))
+    else:
+        S.append(("decoder.embedding.PE.pos_embed.weight", (dec_len, d), "kaiming"))
     stack("decoder.decoder", cfg.n_layers_decode, True)
     lin("decoder.fcn.command_fcn", cfg.n_commands, d)
-    lin("decoder.fcn.args_fcn", cfg.n_args * (cfg.args_dim + 1), d)
+    lin("decoder.fcn.args_fcn", cfg.n_args * out_classes, d)
     return S
 
 
@@ -231,7 +240,9 @@ class SVGTransformer(nn.Module):
         self._gs = None            # the one live _GraphState
         self.graph_kernel_launches = 0   # kernels launched through graph replays (the library's own counter sees captures only)
         self._gs_streak = (None, 0)
-        self.args_dim = cfg.args_dim + 1                      # model.py:293 (rel_targets unsupported)
+        self.rel_targets = bool(getattr(cfg, "rel_targets", False))
+        self.autoregressive = getattr(cfg, "pred_mode", "one_shot") == "autoregressive"
+        self.args_dim = 2 * cfg.args_dim if self.rel_targets else cfg.args_dim + 1      # model.py:293
         self.precision = precision or os.environ.get("DSVG_PRECISION", "bf16")
         if self.precision not in ("bf16", "bf16x3"):
             raise ValueError("precision must be 'bf16' or 'bf16x3'")
@@ -260,7 +271,13 @@ class SVGTransformer(nn.Module):
             if not self.self_match:
                 _register(self, "encoder.hierarchical_PE.position", pos(cfg.max_num_groups), True)
             _register(self, "decoder.hierarchical_embedding.PE.position", pos(cfg.num_groups_proposal), True)
-        _register(self, "decoder.embedding.PE.position", pos(dec_len), True)
+        if self.autoregressive:
+            _register(self, "decoder.embedding.pos_encoding.position", pos(cfg.max_total_len + 2), True)
+            n = cfg.max_total_len + 1                                     # model/utils.py:69-72, registered at model.py:221-222
+            _register(self, "decoder.square_subsequent_mask",
+                      torch.zeros(n, n).masked_fill(torch.triu(torch.ones(n, n, dtype=torch.bool), 1), float("-inf")), True)
+        else:
+            _register(self, "decoder.embedding.PE.position", pos(dec_len), True)
         self.register_buffer("cmd_args_mask", CMD_ARGS_MASK.clone())       # model.py:309
         self._pnames = [n for n, _, _ in self._specs]
         self._sites = {}
@@ -322,6 +339,13 @@ class SVGTransformer(nn.Module):
                 raise ValueError("label ids must lie in [0, n_labels)")
         inputs = dict(commands=commands_enc, args=args_enc, label=label, z=z, encode_mode=encode_mode,
                       return_hierarch=return_hierarch, training=self.training, hierarch_logits=hierarch_logits)
+        if self.autoregressive and not encode_mode:
+            if commands_dec is None or args_dec is None:
+                raise ValueError("the autoregressive decoder needs its input tokens (commands_dec, args_dec)")
+            cd, ad = commands_dec.detach().float(), args_dec.detach().float()
+            if return_tgt:                                   # teacher forcing: the last position is only a target (model.py:372)
+                cd, ad = cd[..., :-1], ad[..., :-1, :]
+            inputs["dec_inputs"] = (cd.contiguous(), ad.contiguous())
         if self.self_match and return_tgt and not encode_mode and not return_hierarch:   # model.py:384
             if commands_dec is None or args_dec is None:
                 raise ValueError("self_match needs the decoder targets (commands_dec, args_dec)")
@@ -357,6 +381,8 @@ class SVGTransformer(nn.Module):
             return outs[0].view(N, Gp, 2).permute(1, 0, 2).unsqueeze(0), outs[1].view(N, Gp, -1).permute(1, 0, 2).unsqueeze(0)
         G = cfg.num_groups_proposal if two else 1
         Ld = (cfg.max_seq_len if two else cfg.max_total_len) + 1
+        if self.autoregressive:
+            Ld = inputs["dec_inputs"][0].shape[-1]
         it = iter(outs)
         res = {"command_logits": next(it).view(N, G, Ld, cfg.n_commands),
                "args_logits": next(it).view(N, G, Ld, cfg.n_args, self.args_dim)}
@@ -403,13 +429,15 @@ class SVGTransformer(nn.Module):
         forward; the token post-processing below is a handful of tiny torch ops (not on the train-step hot path).
         At the reference's default temperature (1e-4) `Categorical(logits / T).sample()` is an argmax up to exact
         ties; temperatures below 1e-3 therefore take the deterministic argmax, larger ones sample."""
-        res = self.forward(commands_enc, args_enc, commands_dec, args_dec, label=label, z=z,
-                           hierarch_logits=hierarch_logits, return_tgt=False)
-
         def pick(logits):
             if temperature < 1e-3:
                 return logits.argmax(dim=-1)
             return torch.distributions.Categorical(logits=logits / temperature).sample()
+
+        if self.autoregressive:
+            return self._greedy_sample_autoregressive(commands_enc, args_enc, label, z, pick, concat_groups)
+        res = self.forward(commands_enc, args_enc, commands_dec, args_dec, label=label, z=z,
+                           hierarch_logits=hierarch_logits, return_tgt=False)
 
         commands_y = pick(res["command_logits"])
         args_y = pick(res["args_logits"]) - 1                               # shift back: class 0 is the -1 PAD value
@@ -423,6 +451,49 @@ class SVGTransformer(nn.Module):
             commands_y = commands_y[keep].reshape(n, -1)
             args_y = args_y[keep].reshape(n, -1, self.cfg.n_args)
         return commands_y, args_y
+
+    def _greedy_sample_autoregressive(self, commands_enc, args_enc, label, z, pick, concat_groups):
+        """model.py:428-448: token-by-token decoding -- every step re-runs the causal decoder on the prefix (the reference does
+        the same; there is no KV cache in either), keeps the last position's tokens, and feeds them back."""
+        cfg = self.cfg
+        if z is None:
+            z = self.forward(commands_enc, args_enc, None, None, label=label, encode_mode=True)      # (1, 1, N, dz)
+            z = z.permute(2, 0, 1, 3)                                                                # batch-first for z=
+        N, dev = z.shape[0], z.device
+        commands_y = torch.full((N, 1, 1), 5, dtype=torch.long, device=dev)                          # SOS
+        args_y = torch.full((N, 1, 1, cfg.n_args), -1, dtype=torch.long, device=dev)
+        for _ in range(cfg.max_total_len):
+            res = self.forward(None, None, commands_y.float(), args_y.float(), label=label, z=z, return_tgt=False)
+            c_new = pick(res["command_logits"])
+            a_new = pick(res["args_logits"]) - 1                                                     # shift back: class 0 = PAD
+            _, a_new = self._make_valid(c_new, a_new)
+            commands_y = torch.cat([commands_y, c_new[..., -1:]], dim=-1)
+            args_y = torch.cat([args_y, a_new[..., -1:, :]], dim=-2)
+        commands_y, args_y = commands_y[..., 1:], args_y[..., 1:, :]                                 # discard SOS
+        if self.rel_targets:
+            args_y = self._make_absolute(commands_y, args_y)
+        if concat_groups:
+            n = commands_y.size(0)
+            keep = (commands_y == 4).cumsum(dim=-1) == 0
+            commands_y = commands_y[keep].reshape(n, -1)
+            args_y = args_y[keep].reshape(n, -1, cfg.n_args)
+        return commands_y, args_y
+
+    def _make_absolute(self, commands_y, args_y):
+        """model.py:461-478: relative argument classes back to absolute coordinates (running sum of the end positions over
+        the real commands, as the reference does over the flattened batch)."""
+        args_y = args_y.clone()
+        mask = self.cmd_args_mask[commands_y].bool()
+        args_y[mask] -= self.cfg.args_dim - 1
+        real = commands_y < 4
+        a = args_y[real]
+        end_pos = a[:-1, 9:11].cumsum(dim=0)
+        a[1:, 5:7] += end_pos
+        a[1:, 7:9] += end_pos
+        a[1:, 9:11] += end_pos
+        args_y[real] = a
+        _, args_y = self._make_valid(commands_y, args_y)
+        return args_y
 
     def _make_valid(self, commands_y, args_y, visibility_y=None, PAD_VAL=-1):
         """model.py:450-459: invisible paths become `m EOS EOS ...` with PAD arguments; argument slots a command does
@@ -490,7 +561,8 @@ class SVGTransformer(nn.Module):
         ops.linear(a, w_in, M, 3 * d, d, bias=P("self_attn.in_proj_bias"), scale_cols=d, scale=float(hd) ** -0.5,
                    out_act=qkv)
         o = Act(M, d, pl, dev)
-        ops.attn_fwd(qkv, key_valid, o, nseq, L, H, hd, self._drop(sv, pre + ".attn"))
+        ops.attn_fwd(qkv, key_valid, o, nseq, L, H, hd, self._drop(sv, pre + ".attn"),
+                     causal=pre.startswith(getattr(sv, "causal_stack", "\0")))
         x1 = torch.empty(M, d, device=dev)
         w_o, _ = self._pack(pre + ".self_attn.out_proj.weight")
         b = Act(M, d, pl, dev)
@@ -733,9 +805,37 @@ class SVGTransformer(nn.Module):
         Ld = (cfg.max_seq_len if two else cfg.max_total_len) + 1
         Md = nseq_d * Ld
         sv.nseq_d, sv.Ld, sv.Md = nseq_d, Ld, Md
-        x = torch.empty(Md, d, device=dev)
-        ops.rows_embed_fwd(None, P("decoder.embedding.PE.pos_embed.weight"), x, Md, Ld, d, self._drop(sv, "dec.pe", 0.1))
-        x, fin = self._stack_fwd(sv, "decoder.decoder", cfg.n_layers_decode, x, Md, Ld, nseq_d, None, zmem=zmem, lab=lab_d,
+        dec_valid = None
+        if self.autoregressive:
+            # ---- autoregressive decoder input (model.py:262-269): the shifted target tokens, embedded with the decoder's own
+            # SVGEmbedding (group index = number of "m" so far), attended causally with the key-padding mask of those tokens
+            cd, ad = inp["dec_inputs"]
+            if cd.shape[0] != N or cd.shape[1] != 1:
+                raise ValueError("autoregressive decoder expects grouped tokens (N, 1, S)")
+            Ld = cd.shape[2]
+            if Ld > cfg.max_total_len + 1:
+                raise ValueError("at most %d decoder positions" % (cfg.max_total_len + 1))
+            Md = nseq_d * Ld
+            sv.Ld, sv.Md = Ld, Md
+            sv.dec_cmd, sv.dec_arg = cd, ad
+            sv.dec_grp = torch.empty(Md, dtype=torch.uint8, device=dev)
+            dec_valid = torch.empty(Md, dtype=torch.uint8, device=dev)
+            ops.seq_prep(cd, nseq_d, Ld, None, None, dec_valid, sv.dec_grp, None)
+            sv.dec_valid = dec_valid
+            Vd, na = self.args_dim, cfg.n_args
+            sv.dec_table = torch.empty(na * Vd, d, device=dev)
+            sv.dec_base = torch.empty(d, device=dev)
+            ops.embed_fold(P("decoder.embedding.arg_embed.weight"), P("decoder.embedding.embed_fcn.weight"),
+                           P("decoder.embedding.embed_fcn.bias"), sv.dec_table, sv.dec_base, Vd, na, d)
+            x = torch.empty(Md, d, device=dev)
+            ops.embed_fwd(cd, ad, sv.dec_grp, P("decoder.embedding.command_embed.weight"), sv.dec_table, sv.dec_base,
+                          P("decoder.embedding.pos_encoding.pos_embed.weight"), P("decoder.embedding.group_embed.weight"), x,
+                          Md, Ld, Vd, na, d, self._drop(sv, "dec.pe", 0.1))
+            sv.causal_stack = "decoder.decoder"
+        else:
+            x = torch.empty(Md, d, device=dev)
+            ops.rows_embed_fwd(None, P("decoder.embedding.PE.pos_embed.weight"), x, Md, Ld, d, self._drop(sv, "dec.pe", 0.1))
+        x, fin = self._stack_fwd(sv, "decoder.decoder", cfg.n_layers_decode, x, Md, Ld, nseq_d, dec_valid, zmem=zmem, lab=lab_d,
                                  lab_rpg=lab_rpg, final_ln=True)
         sv.d1_x = x
         if fin is not None:
@@ -823,7 +923,8 @@ class SVGTransformer(nn.Module):
         _, wot = self._pack(pre + ".self_attn.out_proj.weight")
         ops.linear(dt, wot, M, d, d, out_act=do)
         dqkv = Act(M, 3 * d, pl, dev)
-        ops.attn_bwd(s["qkv"], key_valid, do, dqkv, nseq, L, H, hd, float(hd) ** -0.5, self._drop(sv, pre + ".attn"))
+        ops.attn_bwd(s["qkv"], key_valid, do, dqkv, nseq, L, H, hd, float(hd) ** -0.5, self._drop(sv, pre + ".attn"),
+                     causal=pre.startswith(getattr(sv, "causal_stack", "\0")))
         ops.outer(dqkv, s["a"], M, 3 * d, d, G("self_attn.in_proj_weight"), colsum=G("self_attn.in_proj_bias"))
         _, wit = self._pack(pre + ".self_attn.in_proj_weight")
         dx0 = torch.empty(M, d, device=dev)
@@ -976,10 +1077,20 @@ class SVGTransformer(nn.Module):
                 dx = self._stack_bwd(sv, gd, "decoder.decoder", nl, dx, dxa, Md, Ld, nseq_d, None, zmem=sv.zpath_act,
                                      dzmem=dzp32, lab=sv.lab_d, dlab=dlab_d, lab_rpg=Gp)
             else:
-                dx = self._stack_bwd(sv, gd, "decoder.decoder", nl, dx, dxa, Md, Ld, nseq_d, None, zmem=sv.z_act,
-                                     dzmem=dz32, lab=sv.lab_d, dlab=dlab_d, lab_rpg=1)
-            ops.rows_embed_bwd(dx, None, gd["decoder.embedding.PE.pos_embed.weight"], nseq_d, Ld, d,
-                               self._drop(sv, "dec.pe", 0.1))
+                dx = self._stack_bwd(sv, gd, "decoder.decoder", nl, dx, dxa, Md, Ld, nseq_d, getattr(sv, "dec_valid", None),
+                                     zmem=sv.z_act, dzmem=dz32, lab=sv.lab_d, dlab=dlab_d, lab_rpg=1)
+            if self.autoregressive:
+                Vd, na = self.args_dim, cfg.n_args
+                scratch = torch.empty(na * Vd, d, device=dev)
+                ops.embed_bwd(sv.dec_cmd, sv.dec_arg, sv.dec_grp, dx, P("decoder.embedding.arg_embed.weight"),
+                              P("decoder.embedding.embed_fcn.weight"), gd["decoder.embedding.command_embed.weight"],
+                              gd["decoder.embedding.pos_encoding.pos_embed.weight"], gd["decoder.embedding.group_embed.weight"],
+                              gd["decoder.embedding.arg_embed.weight"], gd["decoder.embedding.embed_fcn.weight"],
+                              gd["decoder.embedding.embed_fcn.bias"], scratch, nseq_d, Ld, Vd, na, d, cfg.max_total_len + 2,
+                              self._drop(sv, "dec.pe", 0.1))
+            else:
+                ops.rows_embed_bwd(dx, None, gd["decoder.embedding.PE.pos_embed.weight"], nseq_d, Ld, d,
+                                   self._drop(sv, "dec.pe", 0.1))
             if two:
                 # ---- D2 heads (basic_blocks.py:33-39) ----
                 dzp = Act(nq, dz, pl, dev)
@@ -1092,7 +1203,7 @@ class SVGTransformer(nn.Module):
     # =================================================================================================
     def _graph_key(self, inp):
         """Input signature a captured graph is valid for, or None when this call is not graphable."""
-        if not self.graphs or self.self_match or not inp["training"] or not inp.get("need_grad", False) or inp["z"] is not None \
+        if not self.graphs or self.self_match or self.autoregressive or not inp["training"] or not inp.get("need_grad", False) or inp["z"] is not None \
                 or inp["encode_mode"] or inp["return_hierarch"] or ops.PROFILE is not None:
             return None
         c, a, lab = inp["commands"], inp["args"], inp["label"]

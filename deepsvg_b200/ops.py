@@ -198,17 +198,17 @@ def ln_bwd(x, mean, rstd, gamma, M, D, *, dy=None, dz=None, valid=None, inv_cnt=
     _lib.check(rc, "dsvg_ln_bwd")
 
 
-def attn_fwd(qkv, key_valid, out, nseq, L, H, hd, drop):
+def attn_fwd(qkv, key_valid, out, nseq, L, H, hd, drop, causal=False):
     with _Prof("attn_fwd", 4.0 * nseq * L * L * H * hd):
-        rc = _lib.load().dsvg_attn_fwd(qkv.ptr, qkv.lo, _p(key_valid), out.ptr, out.lo, nseq, L, H, hd, drop[0],
+        rc = _lib.load().dsvg_attn_fwd(qkv.ptr, qkv.lo, _p(key_valid), out.ptr, out.lo, nseq, L, H, hd, int(causal), drop[0],
                                        drop[1], drop[2], _stream())
     _lib.check(rc, "dsvg_attn_fwd")
 
 
-def attn_bwd(qkv, key_valid, dout, dqkv, nseq, L, H, hd, q_scale, drop):
+def attn_bwd(qkv, key_valid, dout, dqkv, nseq, L, H, hd, q_scale, drop, causal=False):
     with _Prof("attn_bwd", 8.0 * nseq * L * L * H * hd):
         rc = _lib.load().dsvg_attn_bwd(qkv.ptr, qkv.lo, _p(key_valid), dout.ptr, dout.lo, dqkv.ptr, dqkv.lo, nseq, L, H,
-                                       hd, q_scale, drop[0], drop[1], drop[2], _stream())
+                                       hd, int(causal), q_scale, drop[0], drop[1], drop[2], _stream())
     _lib.check(rc, "dsvg_attn_bwd")
 
 

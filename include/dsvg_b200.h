@@ -174,11 +174,14 @@ int dsvg_ln_bwd(const float* x, const float* mean, const float* rstd, const floa
                 const float* dx_in, float* dx_out, dsvg_bf16* dact, size_t dact_lo_off, float drop_p,
                 uint32_t drop_site, uint64_t seed, float* dgamma, float* dbeta, int M, int D, void* stream);
 
-/* ---- self-attention over short sequences (functional.py:168-248) -------------------------------------- */
+/* ---- self-attention over short sequences (functional.py:168-248) --------------------------------------
+ * key_valid (optional, [nseq*L]): key_padding_mask (functional.py:235-240); causal != 0: attn_mask = square_subsequent_mask
+ * (query i sees keys j <= i; model/utils.py:69-72, the autoregressive decoder, model.py:269). */
 int dsvg_attn_fwd(const dsvg_bf16* qkv, size_t qkv_lo_off, const uint8_t* key_valid, dsvg_bf16* out, size_t out_lo_off,
-                  int nseq, int L, int H, int head_dim, float drop_p, uint32_t drop_site, uint64_t seed, void* stream);
+                  int nseq, int L, int H, int head_dim, int causal, float drop_p, uint32_t drop_site, uint64_t seed,
+                  void* stream);
 int dsvg_attn_bwd(const dsvg_bf16* qkv, size_t qkv_lo_off, const uint8_t* key_valid, const dsvg_bf16* dout,
-                  size_t dout_lo_off, dsvg_bf16* dqkv, size_t dqkv_lo_off, int nseq, int L, int H, int head_dim,
+                  size_t dout_lo_off, dsvg_bf16* dqkv, size_t dqkv_lo_off, int nseq, int L, int H, int head_dim, int causal,
                   float q_scale, float drop_p, uint32_t drop_site, uint64_t seed, void* stream);
 
 /* ---- SVGLoss (model/loss.py:19-65): loss sums + unit-scale d(loss)/d(logits) --------------------------- */

@@ -120,11 +120,23 @@ def param_shapes(cfg):
         lin("decoder.hierarchical_fcn.visibility_fcn", 2, d)
         lin("decoder.hierarchical_fcn.z_fcn", dz, d)
     dec_len = (cfg.max_seq_len if two_d else cfg.max_total_len) + 1
-    out["decoder.embedding.PE.pos_embed.weight"] = (dec_len, d)
+    if cfg.pred_mode == "autoregressive":                       # model.py:218-222: the decoder embeds its own (shifted) targets
+        out["decoder.embedding.command_embed.weight"] = (cfg.n_commands, d)
+        out["decoder.embedding.arg_embed.weight"] = (out_args_dim(cfg), 64)
+        lin("decoder.embedding.embed_fcn", d, 64 * cfg.n_args)
+        out["decoder.embedding.group_embed.weight"] = (cfg.max_total_len + 2, d)
+        out["decoder.embedding.pos_encoding.pos_embed.weight"] = (cfg.max_total_len + 2, d)
+    else:
+        out["decoder.embedding.PE.pos_embed.weight"] = (dec_len, d)
     stack("decoder.decoder", cfg.n_layers_decode, True)
     lin("decoder.fcn.command_fcn", cfg.n_commands, d)
-    lin("decoder.fcn.args_fcn", cfg.n_args * (cfg.args_dim + 1), d)
+    lin("decoder.fcn.args_fcn", cfg.n_args * out_args_dim(cfg), d)
     return out
+
+
+def out_args_dim(cfg):
+    """Classes per argument slot (model.py:37,233; loss.py:15): relative targets span -(args_dim-1)..args_dim-1 (+PAD)."""
+    return 2 * cfg.args_dim if cfg.rel_targets else cfg.args_dim + 1
 
 
 def make_params(cfg, seed=0, dtype=torch.float32):
@@ -219,7 +231,7 @@ def _drop(x, p):
     return F.dropout(x, p, training=True) if p > 0 else x
 
 
-def _self_attention(mm, x, p, pre, n_heads, key_pad, drop=0.0):
+def _self_attention(mm, x, p, pre, n_heads, key_pad, drop=0.0, causal=False):
     """functional.py:92-249 for query is key is value.  x [..., L, d]; key_pad bool [..., L] True = ignore key."""
     d = x.shape[-1]
     hd = d // n_heads
@@ -229,6 +241,9 @@ def _self_attention(mm, x, p, pre, n_heads, key_pad, drop=0.0):
     shp = x.shape[:-1] + (n_heads, hd)
     q, k, v = (t.reshape(shp).transpose(-2, -3) for t in (q, k, v))                       # [..., H, L, hd]
     s = mm.mm(q, k.transpose(-1, -2))                                                     # :228
+    if causal:                                                                            # attn_mask = square_subsequent_mask
+        Lq = s.shape[-1]                                                                  # (model/utils.py:69-72; functional.py:229)
+        s = s.masked_fill(torch.triu(torch.ones(Lq, Lq, dtype=torch.bool, device=s.device), 1), float("-inf"))
     if key_pad is not None:
         s = s.masked_fill(key_pad[..., None, None, :], float("-inf"))                     # :235-240
     a = _drop(torch.softmax(s, dim=-1), drop)                                             # :243-244
@@ -236,11 +251,11 @@ def _self_attention(mm, x, p, pre, n_heads, key_pad, drop=0.0):
     return mm.linear(o, p[pre + ".out_proj.weight"], p[pre + ".out_proj.bias"])          # :249
 
 
-def _layer(mm, x, p, pre, n_heads, key_pad, zglob, lab, drop=0.0):
+def _layer(mm, x, p, pre, n_heads, key_pad, zglob, lab, drop=0.0, causal=False):
     """Pre-LN block: improved_transformer.py:42-54 (encoder) / :126-141 (decoder with linear_global).
     zglob / lab broadcast over the sequence axis (-2)."""
     h = x + _drop(_self_attention(mm, _layer_norm(x, p[pre + ".norm1.weight"], p[pre + ".norm1.bias"]), p,
-                                  pre + ".self_attn", n_heads, key_pad, drop), drop)
+                                  pre + ".self_attn", n_heads, key_pad, drop, causal), drop)
     if zglob is not None:
         h = h + _drop(mm.linear(zglob, p[pre + ".linear_global.weight"], p[pre + ".linear_global.bias"]), drop).unsqueeze(-2)
     if lab is not None:
@@ -251,10 +266,10 @@ def _layer(mm, x, p, pre, n_heads, key_pad, zglob, lab, drop=0.0):
     return h + _drop(f, drop)
 
 
-def _stack(mm, x, p, pre, n_layers, n_heads, key_pad=None, zglob=None, lab=None, drop=0.0):
+def _stack(mm, x, p, pre, n_layers, n_heads, key_pad=None, zglob=None, lab=None, drop=0.0, causal=False):
     """transformer.py:168-188 / :214-242: L layers then the final LayerNorm."""
     for i in range(n_layers):
-        x = _layer(mm, x, p, f"{pre}.layers.{i}", n_heads, key_pad, zglob, lab, drop)
+        x = _layer(mm, x, p, f"{pre}.layers.{i}", n_heads, key_pad, zglob, lab, drop, causal)
     return _layer_norm(x, p[pre + ".norm.weight"], p[pre + ".norm.bias"])
 
 
@@ -284,7 +299,8 @@ def group_index(cmd):      # number of "m" so far                  (model/utils.
 # --------------------------------------------------------------------------------------------------
 # forward (model.py:352-412), eval mode (no dropout); VAE noise is an input
 # --------------------------------------------------------------------------------------------------
-def forward(params, cfg, commands, args, label=None, eps=None, matmul="fp32", z_in=None, train_dropout=False):
+def forward(params, cfg, commands, args, label=None, eps=None, matmul="fp32", z_in=None, train_dropout=False,
+            commands_dec=None, args_dec=None):
     """commands [N,G,L] / args [N,G,L,11] float (encoder == decoder inputs, as model/config.py:47-60 wires them).
     Returns the reference's result dict (batch-first) plus 'z' [N, dz].
     train_dropout: draw the reference's train-mode dropout masks (cfg.dropout; 0.1 at the positional encodings,
@@ -359,11 +375,24 @@ def forward(params, cfg, commands, args, label=None, eps=None, matmul="fp32", z_
         zmem, Gd = z[:, None, :], 1
         lab_d1 = None if lab_d is None else lab_d[:, None, :]
     Ld = (cfg.max_seq_len if two_d else cfg.max_total_len) + 1
-    src = _drop(p["decoder.embedding.PE.pos_embed.weight"][:Ld].reshape(1, 1, Ld, -1).expand(N, Gd, Ld, -1), dr_pe)   # :278
-    out = _stack(mm, src, p, "decoder.decoder", cfg.n_layers_decode, H, None, zglob=zmem, lab=lab_d1, drop=dr)        # :279
+    commands_dec = commands if commands_dec is None else commands_dec
+    args_dec = args if args_dec is None else args_dec
+    if cfg.pred_mode == "autoregressive":                                                  # model.py:262-272 (transformer)
+        cd, ad = commands_dec[..., :-1].long(), args_dec[..., :-1, :]                      # teacher forcing: drop the last (:372)
+        Ld = cd.shape[-1]
+        emb = p["decoder.embedding.arg_embed.weight"][(ad + 1).long()].reshape(N, Gd, Ld, -1)
+        src = p["decoder.embedding.command_embed.weight"][cd] + \
+            mm.linear(emb, p["decoder.embedding.embed_fcn.weight"], p["decoder.embedding.embed_fcn.bias"]) + \
+            p["decoder.embedding.group_embed.weight"][group_index(cd)]
+        src = _drop(src + p["decoder.embedding.pos_encoding.pos_embed.weight"][:Ld], dr_pe)
+        out = _stack(mm, src, p, "decoder.decoder", cfg.n_layers_decode, H, key_padding(cd), zglob=zmem, lab=lab_d1, drop=dr,
+                     causal=True)                                                          # :269
+    else:
+        src = _drop(p["decoder.embedding.PE.pos_embed.weight"][:Ld].reshape(1, 1, Ld, -1).expand(N, Gd, Ld, -1), dr_pe)   # :278
+        out = _stack(mm, src, p, "decoder.decoder", cfg.n_layers_decode, H, None, zglob=zmem, lab=lab_d1, drop=dr)        # :279
     res["command_logits"] = mm.linear(out, p["decoder.fcn.command_fcn.weight"], p["decoder.fcn.command_fcn.bias"])
     al = mm.linear(out, p["decoder.fcn.args_fcn.weight"], p["decoder.fcn.args_fcn.bias"])
-    res["args_logits"] = al.reshape(N, Gd, Ld, cfg.n_args, cfg.args_dim + 1)                # basic_blocks.py:21
+    res["args_logits"] = al.reshape(N, Gd, Ld, cfg.n_args, out_args_dim(cfg))               # basic_blocks.py:21
     if getattr(cfg, "self_match", False) and two_d and z_in is None:                        # model.py:384-394
         asg = perfect_matching(res["command_logits"].detach(), res["args_logits"].detach(),
                                res["visibility_logits"].detach(), commands[..., 1:], args[..., 1:, :], cfg)
@@ -372,7 +401,7 @@ def forward(params, cfg, commands, args, label=None, eps=None, matmul="fp32", z_
             t = res[k]
             idx = asg.reshape(asg.shape + (1,) * (t.dim() - 2)).expand_as(t)
             res[k] = torch.gather(t, 1, idx)
-    res["tgt_commands"], res["tgt_args"] = commands, args                                  # model.py:404-405
+    res["tgt_commands"], res["tgt_args"] = commands_dec, args_dec                          # model.py:404-405
     return res
 
 
@@ -455,10 +484,11 @@ def loss(out, cfg, weights=DEFAULT_WEIGHTS):
 
 
 def train_step(params, cfg, commands, args, label=None, eps=None, weights=DEFAULT_WEIGHTS, matmul="fp32",
-               train_dropout=False):
+               train_dropout=False, commands_dec=None, args_dec=None):
     """forward + loss + backward (train.py:94-98; eval-mode arithmetic unless train_dropout).  Returns (out, losses, grads)."""
     leaves = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
-    out = forward(leaves, cfg, commands, args, label=label, eps=eps, matmul=matmul, train_dropout=train_dropout)
+    out = forward(leaves, cfg, commands, args, label=label, eps=eps, matmul=matmul, train_dropout=train_dropout,
+                  commands_dec=commands_dec, args_dec=args_dec)
     ls = loss(out, cfg, weights)
     ls["loss"].backward()
     grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaves.items()}

@@ -82,6 +82,14 @@ CASES = {
                                             use_vae=False, self_match=True), 5, True),
     "selfmatch_d128": ("hierarchical", dict(use_vae=False, d_model=128, n_heads=4, dim_feedforward=256, dim_z=64, n_layers=2,
                                             n_layers_decode=2, max_num_groups=4, max_seq_len=10, self_match=True), 6, False),
+    # Sketchformer (model/config.py:74-80): one-stage, autoregressive decoder (causal mask, embedded shifted targets),
+    # relative argument targets (2 * args_dim classes)
+    "tiny_sketchformer": ("one_stage", dict(d_model=32, n_heads=4, dim_feedforward=64, dim_z=32, n_layers=2,
+                                            n_layers_decode=2, max_num_groups=4, max_total_len=12, args_dim=15,
+                                            use_vae=True, pred_mode="autoregressive", rel_targets=True), 3, True),
+    "sketchformer_d128": ("one_stage", dict(d_model=128, n_heads=4, dim_feedforward=256, dim_z=64, n_layers=2,
+                                            n_layers_decode=2, max_num_groups=4, max_total_len=30, use_vae=False,
+                                            pred_mode="autoregressive", rel_targets=True), 4, False),
 }
 
 
@@ -153,6 +161,13 @@ def run_case(name):
     cmd, arg = edge_batch(cfg_o) if name.startswith("edge") else O.synth_batch(cfg_o, batch, seed=99)
     assert cmd.shape[0] == batch
     cmd, arg = cmd.double(), arg.double()
+    arg_dec = arg
+    if over.get("rel_targets"):
+        # relative-argument targets (SVGTensor.get_relative_args, difflib/tensor.py:150-168): ids in [0, 2*args_dim-2] on
+        # the slots the command uses, -1 elsewhere; drawn at random here (the model only sees them as class ids)
+        m = O.CMD_ARGS_MASK[cmd.long()].double()
+        vals = torch.randint(0, 2 * cfg_o.args_dim - 1, arg.shape, generator=torch.Generator().manual_seed(41)).double()
+        arg_dec = vals * m - (1 - m)
     label = None
     kw = {}
     if cfg_o.label_condition:
@@ -172,7 +187,7 @@ def run_case(name):
             return captured["asg"]
         model.perfect_matching = spy
     try:
-        out = model(cmd, arg, cmd, arg, params={}, **kw)
+        out = model(cmd, arg, cmd, arg_dec, params={}, **kw)
     finally:
         if cfg_o.use_vae:
             torch.randn_like = real
@@ -182,6 +197,8 @@ def run_case(name):
     grads = {k: (p.grad if p.grad is not None else torch.zeros_like(p)) for k, p in model.named_parameters()}
 
     fx = {"commands": cmd.float().numpy(), "args": arg.float().numpy(), "seed_params": np.int64(7)}
+    if arg_dec is not arg:
+        fx["args_dec"] = arg_dec.float().numpy()
     if captured:
         fx["assignment"] = captured["asg"].reshape(batch, -1).numpy()     # what the reference's perfect_matching picked
     if label is not None:

@@ -35,6 +35,13 @@ CASES = {
                                             use_vae=False, self_match=True), True),
     "selfmatch_d128": ("hierarchical", dict(use_vae=False, d_model=128, n_heads=4, dim_feedforward=256, dim_z=64, n_layers=2,
                                             n_layers_decode=2, max_num_groups=4, max_seq_len=10, self_match=True), False),
+    # Sketchformer (model/config.py:74-80): autoregressive decoder, relative argument targets
+    "tiny_sketchformer": ("one_stage", dict(d_model=32, n_heads=4, dim_feedforward=64, dim_z=32, n_layers=2,
+                                            n_layers_decode=2, max_num_groups=4, max_total_len=12, args_dim=15,
+                                            use_vae=True, pred_mode="autoregressive", rel_targets=True), True),
+    "sketchformer_d128": ("one_stage", dict(d_model=128, n_heads=4, dim_feedforward=256, dim_z=64, n_layers=2,
+                                            n_layers_decode=2, max_num_groups=4, max_total_len=30, use_vae=False,
+                                            pred_mode="autoregressive", rel_targets=True), False),
 }
 
 

@@ -56,7 +56,7 @@ def test_config_mirror_and_model_args():
     assert o.get_model_args() == ["commands_grouped", "args_grouped", "commands_grouped", "args_grouped", "label"]
 
 
-@pytest.mark.parametrize("over", [dict(model_type="lstm"), dict(pred_mode="autoregressive"), dict(rel_targets=True),
+@pytest.mark.parametrize("over", [dict(model_type="lstm"), dict(pred_mode="autoregressive"),   # (two-stage autoregressive)
                                   dict(self_match=True, num_groups_proposal=20, max_num_groups=20), dict(d_model=192),
                                   dict(encode_stages=2, decode_stages=1)])
 def test_unsupported_variants_raise_at_construction(over):
@@ -77,6 +77,23 @@ def test_self_matching_variant_is_constructible_and_has_no_path_positional_code(
     assert sorted(k for k, _ in m2.named_parameters()) == list(fx["param_names"])     # names read from the real reference
     with pytest.raises(NotImplementedError):
         SVGTransformer(OneStageOneShot(self_match=True, max_total_len=50))
+
+
+def test_sketchformer_variant_matches_reference_parameter_names():
+    """model/config.py:74-80: autoregressive decoder with its own SVGEmbedding, 2 * args_dim classes (rel_targets)."""
+    from deepsvg_b200 import Sketchformer, SVGTransformer
+    from deepsvg_b200.config import _DefaultConfig
+    cfg, fx, _ = load_case("sketchformer_d128")
+    m = SVGTransformer(_DefaultConfig(**vars(cfg)))
+    assert sorted(k for k, _ in m.named_parameters()) == list(fx["param_names"])     # names read from the real reference
+    sd = m.state_dict()
+    assert tuple(sd["decoder.embedding.arg_embed.weight"].shape) == (512, 64)
+    assert tuple(sd["decoder.fcn.args_fcn.weight"].shape) == (11 * 512, 128)
+    assert tuple(sd["decoder.square_subsequent_mask"].shape) == (31, 31) and sd["decoder.square_subsequent_mask"][0, 1] == float("-inf")
+    assert Sketchformer(max_total_len=50).get_model_args() == ["commands_grouped", "args_grouped", "commands_grouped",
+                                                                "args_rel_grouped"]
+    with pytest.raises(NotImplementedError):     # default Sketchformer: 240-token sequences exceed the attention tile
+        SVGTransformer(Sketchformer())
 
 
 def test_golden_cases_cover_all_reference_branches():

@@ -607,3 +607,35 @@ def test_fused_adamw_matches_torch():
         o_mine.step()
         for a, b in zip(ref, mine):
             assert _rel(b.detach(), a.detach()) < 2e-6
+
+
+# ------------------------------------------------------------------------------------------------ causal attention
+@pytest.mark.parametrize("planes,L,H,hd", [(2, 31, 4, 32), (1, 31, 4, 32), (1, 32, 8, 32), (1, 51, 8, 32), (1, 66, 4, 64),
+                                           (2, 51, 4, 32)])
+def test_attention_causal_with_key_padding(planes, L, H, hd):
+    """attn_mask = square_subsequent_mask plus key_padding_mask (the autoregressive decoder, model.py:264-269;
+    functional.py:229-240) on all three kernels: fp32 SIMT (planes = 2), 32 x 32 mma (L <= 32, head_dim 32), general mma."""
+    ops = _ops()
+    nseq, d = 29, H * hd
+    M = nseq * L
+    qa = ops.act_from_float(_rand(M, 3 * d, seed=1, scale=0.7), planes)
+    qv = qa.float().clone().requires_grad_(True)
+    lens = torch.randint(1, L + 1, (nseq,), generator=torch.Generator().manual_seed(3))
+    vmask = (torch.arange(L)[None, :] < lens[:, None]).to(DEV)
+    valid = vmask.to(torch.uint8).reshape(-1).contiguous()
+    out = ops.Act(M, d, planes, DEV)
+    ops.attn_fwd(qa, valid, out, nseq, L, H, hd, (0.0, 0, 0), causal=True)
+    q, k, v = (t.reshape(nseq, L, H, hd).transpose(1, 2) for t in qv.split(d, dim=-1))
+    s = q @ k.transpose(-1, -2)
+    s = s.masked_fill(torch.triu(torch.ones(L, L, dtype=torch.bool, device=DEV), 1), float("-inf"))
+    s = s.masked_fill(~vmask[:, None, None, :], float("-inf"))
+    ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(M, d)
+    tol = 1e-4 if planes == 2 else 1.5e-2
+    assert _rel(out.float(), ref.detach()) < tol
+    da = ops.act_from_float(_rand(M, d, seed=5), planes)
+    ref.backward(da.float())
+    dqkv = ops.Act(M, 3 * d, planes, DEV)
+    ops.attn_bwd(qa, valid, da, dqkv, nseq, L, H, hd, 1.0, (0.0, 0, 0), causal=True)
+    for lo, hi, nm in ((0, d, "dq"), (d, 2 * d, "dk"), (2 * d, 3 * d, "dv")):
+        e = (dqkv.float()[:, lo:hi] - qv.grad[:, lo:hi]).norm() / qv.grad[:, lo:hi].norm()
+        assert e.item() < tol, (nm, e.item())

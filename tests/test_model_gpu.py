@@ -27,7 +27,7 @@ def _build(cfg_o, precision, seed=7):
     model = SVGTransformer(cfg, precision=precision)
     params = O.make_params(cfg_o, seed=seed)
     missing, unexpected = model.load_state_dict(params, strict=False)
-    assert not unexpected and all(("position" in k or k == "cmd_args_mask") for k in missing)
+    assert not unexpected and all(("position" in k or k in ("cmd_args_mask", "decoder.square_subsequent_mask")) for k in missing)
     return model.to(DEV).eval(), SVGLoss(cfg).to(DEV), params
 
 
@@ -513,3 +513,79 @@ def test_forward_from_hierarch_logits():
         again = model(None, None, None, None, z=zp.permute(2, 1, 0, 3), hierarch_logits=vis, return_tgt=False)
     for k in ("command_logits", "args_logits", "visibility_logits"):
         assert torch.allclose(again[k], full[k], rtol=1e-5, atol=1e-6), k
+
+
+# ------------------------------------------------------------------------------------------------ autoregressive decoder
+def _sketch_inputs(fx):
+    cmd, arg = torch.from_numpy(fx["commands"]), torch.from_numpy(fx["args"])
+    return cmd, arg, torch.from_numpy(fx["args_dec"])
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+def test_sketchformer_matches_reference_golden(precision):
+    """Sketchformer (model/config.py:74-80): one-stage encoder, AUTOREGRESSIVE decoder (its own SVGEmbedding of the shifted
+    targets, causal + key-padding attention), relative argument targets (512 classes) -- against numbers produced by the
+    reference itself."""
+    cfg, fx, _ = load_case("sketchformer_d128")
+    model, loss_fn, _ = _build(cfg, precision, seed=int(fx["seed_params"]))
+    cmd, arg, arg_dec = _sketch_inputs(fx)
+    model.zero_grad(set_to_none=True)
+    c, a, ad = cmd.to(DEV), arg.to(DEV), arg_dec.to(DEV)
+    out = model(c, a, c, ad, params={})
+    ls = loss_fn(out, None, weights=W)
+    ls["loss"].backward()
+    grads = {k: p.grad.detach().cpu() for k, p in model.named_parameters()}
+    assert tuple(out["args_logits"].shape) == tuple(fx["O_shape_args_logits"]) and out["args_logits"].shape[-1] == 512
+    idx = lambda t, n: t.reshape(-1)[torch.linspace(0, t.numel() - 1, n).long().clamp_(max=t.numel() - 1)]
+    if precision == "bf16x3":
+        for k in ("command_logits", "args_logits"):
+            got = idx(out[k].detach().cpu(), 4096) if out[k].numel() > 4096 else out[k].detach().cpu().reshape(-1)
+            np.testing.assert_allclose(got.numpy(), fx["O_" + k].reshape(-1), rtol=1e-3, atol=1e-4, err_msg=k)
+        for k in ("loss", "loss_cmd", "loss_args"):
+            assert abs(ls[k].item() - float(fx["L_" + k])) <= 1e-3 * float(fx["L_" + k]), k
+        for k, g in grads.items():
+            ref_norm = float(fx["Gnorm_" + k])
+            assert abs(g.double().norm().item() - ref_norm) <= 1e-2 * ref_norm + 1e-9, k
+    else:
+        assert abs(ls["loss"].item() - float(fx["L_loss"])) < 2e-2 * float(fx["L_loss"])
+        worst = max(abs(g.double().norm().item() - float(fx["Gnorm_" + k])) / (float(fx["Gnorm_" + k]) + 1e-12)
+                    for k, g in grads.items())
+        assert worst < 0.2, worst
+    assert set(ls) == {"loss", "loss_cmd", "loss_args"}
+
+
+def test_sketchformer_greedy_decoding_is_self_consistent():
+    """model.py:428-448: token-by-token decoding.  Teacher-forcing the ORACLE on the decoded prefix must reproduce every
+    decoded token (wherever the oracle's own top-2 margin is decisive)."""
+    cfg, fx, _ = load_case("sketchformer_d128")
+    model, _, params = _build(cfg, "bf16x3", seed=int(fx["seed_params"]))
+    cmd, arg, _ = _sketch_inputs(fx)
+    c, a = cmd[:2].to(DEV), arg[:2].to(DEV)
+    with torch.no_grad():
+        z = model(c, a, None, None, encode_mode=True).permute(2, 0, 1, 3)        # (N, 1, 1, dz)
+        # the decoding loop of greedy_sample, kept in relative coordinates (no _make_absolute)
+        N, T = 2, cfg.max_total_len
+        cy = torch.full((N, 1, 1), 5, dtype=torch.long, device=DEV)
+        ay = torch.full((N, 1, 1, 11), -1, dtype=torch.long, device=DEV)
+        for _ in range(T):
+            res = model(None, None, cy.float(), ay.float(), z=z, return_tgt=False)
+            cn, an = res["command_logits"].argmax(-1), res["args_logits"].argmax(-1) - 1
+            _, an = model._make_valid(cn, an)
+            cy, ay = torch.cat([cy, cn[..., -1:]], -1), torch.cat([ay, an[..., -1:, :]], -2)
+        # public API: absolute coordinates, SOS dropped
+        cg, ag = model.greedy_sample(c, a, None, None, concat_groups=False)
+    assert cg.shape == (N, 1, T) and ag.shape == (N, 1, T, 11) and torch.equal(cg, cy[..., 1:])
+    # oracle, teacher-forced on [SOS, y_1 .. y_T] (+ one trailing position that forward drops)
+    pad_c = torch.full((N, 1, 1), 4.0)
+    pad_a = torch.full((N, 1, 1, 11), -1.0)
+    cd = torch.cat([cy.cpu().float(), pad_c], -1)
+    ad = torch.cat([ay.cpu().float(), pad_a], -2)
+    zo = O.forward(params, cfg, cmd[:2], arg[:2], commands_dec=cd, args_dec=ad)
+    lc, la = zo["command_logits"][:, :, :T], zo["args_logits"][:, :, :T]
+    t2 = lc.topk(2, -1).values
+    sure = (t2[..., 0] - t2[..., 1]) > 1e-3
+    assert bool(((lc.argmax(-1) == cy.cpu()[..., 1:]) | ~sure).all()) and sure.float().mean().item() > 0.9
+    used = O.CMD_ARGS_MASK[cy.cpu()[..., 1:]].bool()
+    t2 = la.topk(2, -1).values
+    sure_a = ((t2[..., 0] - t2[..., 1]) > 1e-3) & used & sure[..., None]
+    assert bool((((la.argmax(-1) - 1) == ay.cpu()[..., 1:, :]) | ~sure_a).all())

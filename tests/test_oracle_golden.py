@@ -26,7 +26,8 @@ def test_oracle_matches_reference(name):
     cmd, arg = torch.from_numpy(fx["commands"]).double(), torch.from_numpy(fx["args"]).double()
     label = torch.from_numpy(fx["label"]) if "label" in fx else None
     eps = torch.from_numpy(fx["eps"]) if "eps" in fx else None
-    out, losses, grads = O.train_step(params, cfg, cmd, arg, label=label, eps=eps)
+    arg_dec = torch.from_numpy(fx["args_dec"]).double() if "args_dec" in fx else None
+    out, losses, grads = O.train_step(params, cfg, cmd, arg, label=label, eps=eps, args_dec=arg_dec)
     for k in ("command_logits", "args_logits", "visibility_logits", "mu", "logsigma"):
         if "O_" + k not in fx:
             assert k not in out
