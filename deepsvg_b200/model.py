@@ -684,9 +684,17 @@ class SVGTransformer(nn.Module):
                 lab_e = Act(N, cfg.dim_label, pl, dev)
                 ops.gather_rows(P("encoder.label_embedding.label_embedding.weight"), label, N, cfg.dim_label, lab_e)
             sv.lab_e = lab_e
+            # path-level stack: the reference repeats the label per path BEFORE linear_global2 + dropout (model.py:123), so
+            # every (path, icon) draws its own dropout mask: one label row per path here too
+            lab_e1, sv.label_e1 = lab_e, label
+            if cfg.label_condition and G > 1:
+                sv.label_e1 = label.repeat_interleave(G)
+                lab_e1 = Act(nseq, cfg.dim_label, pl, dev)
+                ops.gather_rows(P("encoder.label_embedding.label_embedding.weight"), sv.label_e1, nseq, cfg.dim_label, lab_e1)
+            sv.lab_e1 = lab_e1
             # ---- E1 (model.py:135-137) ----
-            x, _ = self._stack_fwd(sv, "encoder.encoder", cfg.n_layers, x, M1, L, nseq, sv.key_valid, lab=lab_e,
-                                   lab_rows_per_group=G * L)
+            x, _ = self._stack_fwd(sv, "encoder.encoder", cfg.n_layers, x, M1, L, nseq, sv.key_valid, lab=lab_e1,
+                                   lab_rows_per_group=L)
             sv.e1_x = x
             zp = torch.empty(nseq, d, device=dev)
             sv.e1_mean, sv.e1_rstd = torch.empty(M1, device=dev), torch.empty(M1, device=dev)
@@ -835,8 +843,14 @@ class SVGTransformer(nn.Module):
         else:
             x = torch.empty(Md, d, device=dev)
             ops.rows_embed_fwd(None, P("decoder.embedding.PE.pos_embed.weight"), x, Md, Ld, d, self._drop(sv, "dec.pe", 0.1))
-        x, fin = self._stack_fwd(sv, "decoder.decoder", cfg.n_layers_decode, x, Md, Ld, nseq_d, dec_valid, zmem=zmem, lab=lab_d,
-                                 lab_rpg=lab_rpg, final_ln=True)
+        lab_d1, sv.label_d1 = lab_d, label
+        if cfg.label_condition and two:                       # model.py:255: the label is repeated per predicted path
+            sv.label_d1 = label.repeat_interleave(lab_rpg)
+            lab_d1 = Act(nseq_d, cfg.dim_label, pl, dev)
+            ops.gather_rows(P("decoder.label_embedding.label_embedding.weight"), sv.label_d1, nseq_d, cfg.dim_label, lab_d1)
+        sv.lab_d1 = lab_d1
+        x, fin = self._stack_fwd(sv, "decoder.decoder", cfg.n_layers_decode, x, Md, Ld, nseq_d, dec_valid, zmem=zmem, lab=lab_d1,
+                                 lab_rpg=1, final_ln=True)
         sv.d1_x = x
         if fin is not None:
             y, sv.d1_mean, sv.d1_rstd = fin
@@ -1074,8 +1088,12 @@ class SVGTransformer(nn.Module):
                 Gp = cfg.num_groups_proposal
                 nq = N * Gp
                 dzp32 = torch.zeros(nq, dz, device=dev)
+                dlab_d1 = torch.zeros(nq, cfg.dim_label, device=dev) if cfg.label_condition else None
                 dx = self._stack_bwd(sv, gd, "decoder.decoder", nl, dx, dxa, Md, Ld, nseq_d, None, zmem=sv.zpath_act,
-                                     dzmem=dzp32, lab=sv.lab_d, dlab=dlab_d, lab_rpg=Gp)
+                                     dzmem=dzp32, lab=sv.lab_d1, dlab=dlab_d1, lab_rpg=1)
+                if cfg.label_condition:
+                    ops.scatter_rows(dlab_d1, sv.label_d1, nq, cfg.dim_label,
+                                     gd["decoder.label_embedding.label_embedding.weight"])
             else:
                 dx = self._stack_bwd(sv, gd, "decoder.decoder", nl, dx, dxa, Md, Ld, nseq_d, getattr(sv, "dec_valid", None),
                                      zmem=sv.z_act, dzmem=dz32, lab=sv.lab_d, dlab=dlab_d, lab_rpg=1)
@@ -1184,8 +1202,13 @@ class SVGTransformer(nn.Module):
                        valid=sv.key_valid, inv_cnt=sv.e1_icnt, L=L, dx_out=dx, dact=dxa,
                        drop=self._drop(sv, "encoder.encoder.layers.%d.drop2" % (nl - 1)),
                        dgamma=gd["encoder.encoder.norm.weight"], dbeta=gd["encoder.encoder.norm.bias"])
-            dx = self._stack_bwd(sv, gd, "encoder.encoder", nl, dx, dxa, M1, L, nseq, sv.key_valid, lab=sv.lab_e,
-                                 dlab=dlab_e, lab_rows_per_group=G * L)
+            dlab_e1 = dlab_e
+            if cfg.label_condition and G > 1:
+                dlab_e1 = torch.zeros(nseq, cfg.dim_label, device=dev)
+            dx = self._stack_bwd(sv, gd, "encoder.encoder", nl, dx, dxa, M1, L, nseq, sv.key_valid, lab=sv.lab_e1,
+                                 dlab=dlab_e1, lab_rows_per_group=L)
+            if cfg.label_condition and G > 1:
+                ops.scatter_rows(dlab_e1, sv.label_e1, nseq, cfg.dim_label, gd["encoder.label_embedding.label_embedding.weight"])
             V, na = cfg.args_dim + 1, cfg.n_args
             scratch = torch.empty(na * V, d, device=dev)
             ops.embed_bwd(sv.commands, sv.args, sv.grp, dx, P("encoder.embedding.arg_embed.weight"),
