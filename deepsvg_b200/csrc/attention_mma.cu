@@ -389,6 +389,295 @@ __global__ void __launch_bounds__(kMmaWarps * 32) attn_mma_bwd_kernel(MmaAttnArg
   }
 }
 
+
+// ================================================================================================================
+// Parity mode ("bf16x3") on the same 32 x 32 tiles: every activation is a (hi, lo) pair of bf16 planes carrying ~16
+// mantissa bits, and every product X . Y is evaluated as Xh.Yh + Xh.Yl + Xl.Yh with fp32 accumulation (the dropped
+// Xl.Yl term is 2^-16 of the product) -- the operand format and arithmetic of the bf16x3 GEMMs.  Probabilities and dS
+// are produced in fp32 registers and split into (hi, lo) before they become operands.  Replaces the fp32 SIMT kernel
+// (attention.cu) for two-plane tensors at head_dim 32, L <= 32: parity mode spent 16 of its 44 ms per step there.
+// ================================================================================================================
+constexpr int kX3Warps = 2;
+constexpr int kX3FwdTiles = 6;    // Qh Ql Kh Kl Vh Vl
+constexpr int kX3BwdTiles = 10;   // + Gh Gl Ph Pl ; dS (hi, lo) overlays V once dP = dO . V^T is in registers
+
+__device__ __forceinline__ uint32_t pack_lo(float a, float b, uint32_t hi) {
+  const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&hi);
+  const float2 hf = __bfloat1622float2(h);
+  return pack_bf16(a - hf.x, b - hf.y);
+}
+// S += X . Y^T over hi/lo planes (tiles row-major [row][channel]; the lo tile follows its hi tile)
+__device__ __forceinline__ void qk_scores_x3(float (&s)[2][4][4], uint32_t x_t, uint32_t y_t, int lane) {
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[mt][nt][e] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    uint32_t ah[2][4], al[2][4];
+    load_a(ah[0], x_t, 0, ks, lane);
+    load_a(ah[1], x_t, 1, ks, lane);
+    load_a(al[0], x_t + kTile * 2, 0, ks, lane);
+    load_a(al[1], x_t + kTile * 2, 1, ks, lane);
+#pragma unroll
+    for (int np = 0; np < 2; ++np) {
+      uint32_t bh[4], bl[4];
+      load_b_nk(bh, y_t, np, ks, lane);
+      load_b_nk(bl, y_t + kTile * 2, np, ks, lane);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        mma_bf16(s[mt][2 * np], al[mt], bh[0], bh[1]);
+        mma_bf16(s[mt][2 * np], ah[mt], bl[0], bl[1]);
+        mma_bf16(s[mt][2 * np], ah[mt], bh[0], bh[1]);
+        mma_bf16(s[mt][2 * np + 1], al[mt], bh[2], bh[3]);
+        mma_bf16(s[mt][2 * np + 1], ah[mt], bl[2], bl[3]);
+        mma_bf16(s[mt][2 * np + 1], ah[mt], bh[2], bh[3]);
+      }
+    }
+  }
+}
+__device__ __forceinline__ void c_to_a_x3(uint32_t (&ah)[4], uint32_t (&al)[4], const float (&c)[2][4][4], int mt, int ks) {
+  c_to_a(ah, c, mt, ks);
+  al[0] = pack_lo(c[mt][2 * ks][0], c[mt][2 * ks][1], ah[0]);
+  al[1] = pack_lo(c[mt][2 * ks][2], c[mt][2 * ks][3], ah[1]);
+  al[2] = pack_lo(c[mt][2 * ks + 1][0], c[mt][2 * ks + 1][1], ah[2]);
+  al[3] = pack_lo(c[mt][2 * ks + 1][2], c[mt][2 * ks + 1][3], ah[3]);
+}
+// out = A(fp32 registers, split here) . Y   with Y (hi, lo) row-major [k][n] in smem
+__device__ __forceinline__ void mul_regs_kn_x3(float (&o)[2][4][4], const float (&p)[2][4][4], uint32_t y_t, int lane) {
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[mt][nt][e] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    uint32_t ah[2][4], al[2][4];
+    c_to_a_x3(ah[0], al[0], p, 0, ks);
+    c_to_a_x3(ah[1], al[1], p, 1, ks);
+#pragma unroll
+    for (int np = 0; np < 2; ++np) {
+      uint32_t bh[4], bl[4];
+      load_b_kn(bh, y_t, np, ks, lane);
+      load_b_kn(bl, y_t + kTile * 2, np, ks, lane);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        mma_bf16(o[mt][2 * np], al[mt], bh[0], bh[1]);
+        mma_bf16(o[mt][2 * np], ah[mt], bl[0], bl[1]);
+        mma_bf16(o[mt][2 * np], ah[mt], bh[0], bh[1]);
+        mma_bf16(o[mt][2 * np + 1], al[mt], bh[2], bh[3]);
+        mma_bf16(o[mt][2 * np + 1], ah[mt], bl[2], bl[3]);
+        mma_bf16(o[mt][2 * np + 1], ah[mt], bh[2], bh[3]);
+      }
+    }
+  }
+}
+// out = Z^T . Y   with Z, Y (hi, lo) row-major [k][.] in smem
+__device__ __forceinline__ void mul_t_kn_x3(float (&o)[2][4][4], uint32_t z_t, uint32_t y_t, int lane) {
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[mt][nt][e] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    uint32_t ah[2][4], al[2][4];
+    load_a_t(ah[0], z_t, 0, ks, lane);
+    load_a_t(ah[1], z_t, 1, ks, lane);
+    load_a_t(al[0], z_t + kTile * 2, 0, ks, lane);
+    load_a_t(al[1], z_t + kTile * 2, 1, ks, lane);
+#pragma unroll
+    for (int np = 0; np < 2; ++np) {
+      uint32_t bh[4], bl[4];
+      load_b_kn(bh, y_t, np, ks, lane);
+      load_b_kn(bl, y_t + kTile * 2, np, ks, lane);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        mma_bf16(o[mt][2 * np], al[mt], bh[0], bh[1]);
+        mma_bf16(o[mt][2 * np], ah[mt], bl[0], bl[1]);
+        mma_bf16(o[mt][2 * np], ah[mt], bh[0], bh[1]);
+        mma_bf16(o[mt][2 * np + 1], al[mt], bh[2], bh[3]);
+        mma_bf16(o[mt][2 * np + 1], ah[mt], bl[2], bl[3]);
+        mma_bf16(o[mt][2 * np + 1], ah[mt], bh[2], bh[3]);
+      }
+    }
+  }
+}
+// C-fragment -> (hi, lo) planes in global memory, rows i < L
+__device__ __forceinline__ void store_c_global_x3(bf16* dst, size_t lo_off, int ld, int L, const float (&c)[2][4][4],
+                                                  float mul, int g, int t) {
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int hrow = 0; hrow < 2; ++hrow) {
+      const int i = 16 * mt + g + 8 * hrow;
+      if (i < L) {
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const float x = c[mt][nt][2 * hrow] * mul, y = c[mt][nt][2 * hrow + 1] * mul;
+          const uint32_t hi = pack_bf16(x, y);
+          bf16* p = dst + size_t(i) * ld + 8 * nt + 2 * t;
+          *reinterpret_cast<uint32_t*>(p) = hi;
+          *reinterpret_cast<uint32_t*>(p + lo_off) = pack_lo(x, y, hi);
+        }
+      }
+    }
+}
+// C-fragment -> (hi, lo) tiles in shared memory (lo tile follows the hi tile)
+__device__ __forceinline__ void store_c_smem_x3(bf16* tile, const float (&c)[2][4][4], int g, int t) {
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int hrow = 0; hrow < 2; ++hrow) {
+      const int i = 16 * mt + g + 8 * hrow;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const uint32_t hi = pack_bf16(c[mt][nt][2 * hrow], c[mt][nt][2 * hrow + 1]);
+        bf16* p = tile + i * kRow + 8 * nt + 2 * t;
+        *reinterpret_cast<uint32_t*>(p) = hi;
+        *reinterpret_cast<uint32_t*>(p + kTile) = pack_lo(c[mt][nt][2 * hrow], c[mt][nt][2 * hrow + 1], hi);
+      }
+    }
+}
+
+struct X3AttnArgs {
+  MmaAttnArgs m;
+  size_t qkv_lo, out_lo, dout_lo, dqkv_lo;   // element offsets of the lo planes
+};
+
+__global__ void __launch_bounds__(kX3Warps * 32) attn_x3_fwd_kernel(X3AttnArgs x) {
+  pdl_launch_dependents();
+  pdl_wait();
+  MmaAttnArgs& a = x.m;
+  drop_resolve(a.drop);
+  extern __shared__ __align__(16) bf16 sm_dyn[];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int L = a.L, d = a.H * 32, ld = 3 * d;
+  bf16* Qs = sm_dyn + wib * kX3FwdTiles * kTile;   // hi tile, lo tile
+  bf16* Ks = Qs + 2 * kTile;
+  bf16* Vs = Ks + 2 * kTile;
+  const uint32_t q_t = smem_addr(Qs), k_t = smem_addr(Ks), v_t = smem_addr(Vs);
+  const long long npairs = (long long)a.nseq * a.H;
+  for (long long pair = (long long)blockIdx.x * kX3Warps + wib; pair < npairs; pair += (long long)gridDim.x * kX3Warps) {
+    const int seq = int(pair / a.H), h = int(pair % a.H);
+    const size_t row0 = size_t(seq) * L;
+    const bf16* base = a.qkv + row0 * ld + h * 32;
+    stage_tile(Qs, base, ld, L, lane);
+    stage_tile(Qs + kTile, base + x.qkv_lo, ld, L, lane);
+    stage_tile(Ks, base + d, ld, L, lane);
+    stage_tile(Ks + kTile, base + d + x.qkv_lo, ld, L, lane);
+    stage_tile(Vs, base + 2 * d, ld, L, lane);
+    stage_tile(Vs + kTile, base + 2 * d + x.qkv_lo, ld, L, lane);
+    const uint32_t kmask = key_mask_of(a.valid, row0, L, lane);
+    __syncwarp();
+    float s[2][4][4];
+    qk_scores_x3(s, q_t, k_t, lane);
+    softmax_rows(s, kmask, t, g, a.causal);
+    if (a.drop.p > 0.f) {
+      float mult[2][4][4];
+      dropout_tile(mult, a.drop, (unsigned long long)pair, g, t);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) s[mt][nt][e] *= mult[mt][nt][e];
+    }
+    float o[2][4][4];
+    mul_regs_kn_x3(o, s, v_t, lane);
+    store_c_global_x3(a.out + row0 * d + h * 32, x.out_lo, d, L, o, 1.f, g, t);
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(kX3Warps * 32) attn_x3_bwd_kernel(X3AttnArgs x) {
+  pdl_launch_dependents();
+  pdl_wait();
+  MmaAttnArgs& a = x.m;
+  drop_resolve(a.drop);
+  extern __shared__ __align__(16) bf16 sm_dyn[];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int L = a.L, d = a.H * 32, ld = 3 * d;
+  bf16* Qs = sm_dyn + wib * kX3BwdTiles * kTile;
+  bf16* Ks = Qs + 2 * kTile;
+  bf16* Vs = Ks + 2 * kTile;
+  bf16* Gs = Vs + 2 * kTile;   // dO
+  bf16* Ps = Gs + 2 * kTile;   // dropout-scaled probabilities
+  bf16* Ds = Vs;               // dS: V is dead once dP is in registers
+  const uint32_t q_t = smem_addr(Qs), k_t = smem_addr(Ks), v_t = smem_addr(Vs), g_t = smem_addr(Gs),
+                 p_t = smem_addr(Ps), d_t = smem_addr(Ds);
+  const long long npairs = (long long)a.nseq * a.H;
+  for (long long pair = (long long)blockIdx.x * kX3Warps + wib; pair < npairs; pair += (long long)gridDim.x * kX3Warps) {
+    const int seq = int(pair / a.H), h = int(pair % a.H);
+    const size_t row0 = size_t(seq) * L;
+    const bf16* base = a.qkv + row0 * ld + h * 32;
+    const bf16* gbase = a.dout + row0 * d + h * 32;
+    stage_tile(Qs, base, ld, L, lane);
+    stage_tile(Qs + kTile, base + x.qkv_lo, ld, L, lane);
+    stage_tile(Ks, base + d, ld, L, lane);
+    stage_tile(Ks + kTile, base + d + x.qkv_lo, ld, L, lane);
+    stage_tile(Vs, base + 2 * d, ld, L, lane);
+    stage_tile(Vs + kTile, base + 2 * d + x.qkv_lo, ld, L, lane);
+    stage_tile(Gs, gbase, d, L, lane);
+    stage_tile(Gs + kTile, gbase + x.dout_lo, d, L, lane);
+    const uint32_t kmask = key_mask_of(a.valid, row0, L, lane);
+    __syncwarp();
+    float p[2][4][4], dp[2][4][4];
+    qk_scores_x3(p, q_t, k_t, lane);
+    softmax_rows(p, kmask, t, g, a.causal);
+    qk_scores_x3(dp, g_t, v_t, lane);          // dP = dO . V^T
+    __syncwarp();                              // every lane is done with V before dS overwrites it
+    if (a.drop.p > 0.f) {
+      float mult[2][4][4];
+      dropout_tile(mult, a.drop, (unsigned long long)pair, g, t);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            dp[mt][nt][e] *= mult[mt][nt][e];
+            mult[mt][nt][e] *= p[mt][nt][e];
+          }
+      store_c_smem_x3(Ps, mult, g, t);
+    } else {
+      store_c_smem_x3(Ps, p, g, t);
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int hrow = 0; hrow < 2; ++hrow) {
+        float delta = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) delta = fmaf(dp[mt][nt][2 * hrow + e], p[mt][nt][2 * hrow + e], delta);
+        delta += __shfl_xor_sync(0xffffffffu, delta, 1);
+        delta += __shfl_xor_sync(0xffffffffu, delta, 2);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+            dp[mt][nt][2 * hrow + e] = p[mt][nt][2 * hrow + e] * (dp[mt][nt][2 * hrow + e] - delta);
+      }
+    store_c_smem_x3(Ds, dp, g, t);
+    __syncwarp();
+    float o[2][4][4];
+    bf16* dbase = a.dqkv + row0 * ld + h * 32;
+    mul_regs_kn_x3(o, dp, k_t, lane);              // dQ = dS . K
+    store_c_global_x3(dbase, x.dqkv_lo, ld, L, o, a.scale, g, t);
+    mul_t_kn_x3(o, d_t, q_t, lane);                // dK = dS^T . Q
+    store_c_global_x3(dbase + d, x.dqkv_lo, ld, L, o, 1.f, g, t);
+    mul_t_kn_x3(o, p_t, g_t, lane);                // dV = (dropout(P))^T . dO
+    store_c_global_x3(dbase + 2 * d, x.dqkv_lo, ld, L, o, 1.f, g, t);
+    __syncwarp();
+  }
+}
+
 }  // namespace dsvg
 using namespace dsvg;
 
@@ -430,6 +719,38 @@ int dsvg_attn_mma_bwd(const bf16* qkv, const uint8_t* valid, const bf16* dout, b
   long long blocks = ((long long)nseq * H + kMmaWarps - 1) / kMmaWarps;
   if (blocks > mma_grid_cap(true)) blocks = mma_grid_cap(true);
   DSVG_CUDA(launch_k(attn_mma_bwd_kernel, dim3(int(blocks)), dim3(kMmaWarps * 32), size_t(smem), st, a));
+  ++g_launches;
+  return 0;
+}
+
+// Parity-mode (two-plane) entry point of the 32 x 32 kernels.
+int dsvg_attn_x3(bool bwd, const bf16* qkv, size_t qkv_lo, const uint8_t* valid, bf16* out, size_t out_lo, const bf16* dout,
+                 size_t dout_lo, bf16* dqkv, size_t dqkv_lo, int nseq, int L, int H, float q_scale, Dropout drop, int causal,
+                 cudaStream_t st) {
+  X3AttnArgs x{};
+  MmaAttnArgs& a = x.m;
+  a.qkv = qkv; a.valid = valid; a.out = out; a.dout = dout; a.dqkv = dqkv; a.nseq = nseq; a.L = L; a.H = H;
+  a.scale = q_scale; a.drop = drop; a.causal = causal;
+  x.qkv_lo = qkv_lo; x.out_lo = out_lo; x.dout_lo = dout_lo; x.dqkv_lo = dqkv_lo;
+  const int smem = kX3Warps * (bwd ? kX3BwdTiles : kX3FwdTiles) * kTile * 2;
+  static bool configured[kMaxDevices] = {};
+  static long long cap[2] = {0, 0};
+  if (first_use_on_device(configured)) {
+    DSVG_CUDA(cudaFuncSetAttribute(attn_x3_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   kX3Warps * kX3FwdTiles * kTile * 2));
+    DSVG_CUDA(cudaFuncSetAttribute(attn_x3_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   kX3Warps * kX3BwdTiles * kTile * 2));
+  }
+  if (cap[bwd] == 0) {
+    int n = 0;
+    if (bwd) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, attn_x3_bwd_kernel, kX3Warps * 32, size_t(smem));
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, attn_x3_fwd_kernel, kX3Warps * 32, size_t(smem));
+    cap[bwd] = 148LL * (n > 0 ? n : 4);
+  }
+  long long blocks = ((long long)nseq * H + kX3Warps - 1) / kX3Warps;
+  if (blocks > cap[bwd]) blocks = cap[bwd];
+  if (bwd) DSVG_CUDA(launch_k(attn_x3_bwd_kernel, dim3(int(blocks)), dim3(kX3Warps * 32), size_t(smem), st, x));
+  else DSVG_CUDA(launch_k(attn_x3_fwd_kernel, dim3(int(blocks)), dim3(kX3Warps * 32), size_t(smem), st, x));
   ++g_launches;
   return 0;
 }
