@@ -261,6 +261,9 @@ int dsvg_attn_gmma(bool bwd, const bf16* qkv, const uint8_t* valid, bf16* out, c
 int dsvg_attn_x3(bool bwd, const bf16* qkv, size_t qkv_lo, const uint8_t* valid, bf16* out, size_t out_lo, const bf16* dout,
                  size_t dout_lo, bf16* dqkv, size_t dqkv_lo, int nseq, int L, int H, float q_scale, Dropout drop, int causal,
                  cudaStream_t st);
+int dsvg_attn_gx3(bool bwd, const bf16* qkv, size_t qkv_lo, const uint8_t* valid, bf16* out, size_t out_lo, const bf16* dout,
+                  size_t dout_lo, bf16* dqkv, size_t dqkv_lo, int nseq, int L, int H, int head_dim, float q_scale, Dropout drop,
+                  int causal, cudaStream_t st);
 static bool attn_simt_forced() {
   static const bool off = [] { const char* e = getenv("DSVG_ATTN"); return e && e[0] == 's'; }();  // "simt"
   return off;
@@ -271,6 +274,9 @@ static bool use_mma(bool single_plane, int L, int head_dim) {
 // parity mode (two planes everywhere) on the same 32 x 32 tiles: three bf16 products per contraction step
 static bool use_x3(bool two_planes, int L, int head_dim) {
   return !attn_simt_forced() && two_planes && head_dim == 32 && L <= 32;
+}
+static bool use_gx3(bool two_planes, int L, int head_dim) {
+  return !attn_simt_forced() && two_planes && (head_dim == 32 || head_dim == 64) && L <= 80;
 }
 // general tensor-core kernel (attention_mma.cu): every other fast-mode shape of the BASELINE configs
 static bool use_gmma(bool single_plane, int L, int head_dim) {
@@ -292,6 +298,9 @@ extern "C" int dsvg_attn_fwd(const dsvg_bf16* qkv, size_t qkv_lo_off, const uint
   if (use_x3(qkv_lo_off != 0 && out_lo_off != 0, L, head_dim))
     return dsvg_attn_x3(false, a.qkv, qkv_lo_off, key_valid, a.out, out_lo_off, nullptr, 0, nullptr, 0, nseq, L, H, 1.f,
                         a.drop, a.causal, st);
+  if (use_gx3(qkv_lo_off != 0 && out_lo_off != 0, L, head_dim))
+    return dsvg_attn_gx3(false, a.qkv, qkv_lo_off, key_valid, a.out, out_lo_off, nullptr, 0, nullptr, 0, nseq, L, H, head_dim,
+                         1.f, a.drop, a.causal, st);
   if (use_gmma(qkv_lo_off == 0 && out_lo_off == 0, L, head_dim))
     return dsvg_attn_gmma(false, a.qkv, key_valid, a.out, nullptr, nullptr, nseq, L, H, head_dim, 1.f, a.drop, a.causal, st);
   if (head_dim == 32) return launch_attn<32>(false, a, st);
@@ -317,6 +326,9 @@ extern "C" int dsvg_attn_bwd(const dsvg_bf16* qkv, size_t qkv_lo_off, const uint
   if (use_x3(qkv_lo_off != 0 && dout_lo_off != 0 && dqkv_lo_off != 0, L, head_dim))
     return dsvg_attn_x3(true, a.qkv, qkv_lo_off, key_valid, nullptr, 0, a.dout, dout_lo_off, a.dqkv, dqkv_lo_off, nseq, L, H,
                         q_scale, a.drop, a.causal, st);
+  if (use_gx3(qkv_lo_off != 0 && dout_lo_off != 0 && dqkv_lo_off != 0, L, head_dim))
+    return dsvg_attn_gx3(true, a.qkv, qkv_lo_off, key_valid, nullptr, 0, a.dout, dout_lo_off, a.dqkv, dqkv_lo_off, nseq, L, H,
+                         head_dim, q_scale, a.drop, a.causal, st);
   if (use_gmma(qkv_lo_off == 0 && dout_lo_off == 0 && dqkv_lo_off == 0, L, head_dim))
     return dsvg_attn_gmma(true, a.qkv, key_valid, nullptr, a.dout, a.dqkv, nseq, L, H, head_dim, q_scale, a.drop, a.causal, st);
   if (head_dim == 32) return launch_attn<32>(true, a, st);

@@ -1186,6 +1186,309 @@ static int launch_gmma_nt(bool bwd, const MmaAttnArgs& a, cudaStream_t st) {
   }
 }
 
+
+// ----------------------------------------------------------------------------------------------------------------
+// Parity mode (two bf16 planes, three products per contraction) of the general kernels: same tiling, every operand tile
+// followed by its lo tile, probabilities / dS split into (hi, lo) when they become operands.  Replaces the fp32 SIMT
+// kernels for BASELINE configs[3] / [4] in bf16x3 (scaled hierarchical: 794 ms per parity step, most of it SIMT attention).
+// ----------------------------------------------------------------------------------------------------------------
+template <int HD, int NT>
+struct GX3 {
+  using G = GAttn<HD, NT>;
+  static constexpr int kSmemFwd = 6 * G::kTileH * 2 + G::LP;
+  static constexpr int kSmemBwd = 8 * G::kTileH * 2 + 4 * G::kTileP * 2 + G::LP;
+};
+#define DSVG_MMA3(acc, ah, al, bh, bl, i, j)   \
+  mma_bf16(acc, al, bh[i], bh[j]);              \
+  mma_bf16(acc, ah, bl[i], bl[j]);              \
+  mma_bf16(acc, ah, bh[i], bh[j])
+
+template <int HD, int NT>
+__device__ __forceinline__ void gx3_scores(float (&s)[2 * NT][4], uint32_t x_tile, uint32_t y_tile, int w, int lane) {
+  using G = GAttn<HD, NT>;
+  constexpr uint32_t kLo = G::kTileH * 2;
+#pragma unroll
+  for (int nt = 0; nt < 2 * NT; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) s[nt][e] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < HD / 16; ++ks) {
+    uint32_t ah[4], al[4];
+    g_load_a(ah, x_tile, 16 * w, 16 * ks, G::SH, lane);
+    g_load_a(al, x_tile + kLo, 16 * w, 16 * ks, G::SH, lane);
+#pragma unroll
+    for (int np = 0; np < NT; ++np) {
+      uint32_t bh[4], bl[4];
+      g_load_b_nk(bh, y_tile, 16 * np, 16 * ks, G::SH, lane);
+      g_load_b_nk(bl, y_tile + kLo, 16 * np, 16 * ks, G::SH, lane);
+      DSVG_MMA3(s[2 * np], ah, al, bh, bl, 0, 1);
+      DSVG_MMA3(s[2 * np + 1], ah, al, bh, bl, 2, 3);
+    }
+  }
+}
+template <int HD, int NT>
+__device__ __forceinline__ void gx3_mul_regs(float (&o)[HD / 8][4], const float (&p)[2 * NT][4], uint32_t y_tile, int lane) {
+  using G = GAttn<HD, NT>;
+  constexpr uint32_t kLo = G::kTileH * 2;
+#pragma unroll
+  for (int nt = 0; nt < HD / 8; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[nt][e] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < NT; ++ks) {
+    uint32_t ah[4], al[4];
+    ah[0] = pack_bf16(p[2 * ks][0], p[2 * ks][1]);
+    ah[1] = pack_bf16(p[2 * ks][2], p[2 * ks][3]);
+    ah[2] = pack_bf16(p[2 * ks + 1][0], p[2 * ks + 1][1]);
+    ah[3] = pack_bf16(p[2 * ks + 1][2], p[2 * ks + 1][3]);
+    al[0] = pack_lo(p[2 * ks][0], p[2 * ks][1], ah[0]);
+    al[1] = pack_lo(p[2 * ks][2], p[2 * ks][3], ah[1]);
+    al[2] = pack_lo(p[2 * ks + 1][0], p[2 * ks + 1][1], ah[2]);
+    al[3] = pack_lo(p[2 * ks + 1][2], p[2 * ks + 1][3], ah[3]);
+#pragma unroll
+    for (int np = 0; np < HD / 16; ++np) {
+      uint32_t bh[4], bl[4];
+      g_load_b_kn(bh, y_tile, 16 * np, 16 * ks, G::SH, lane);
+      g_load_b_kn(bl, y_tile + kLo, 16 * np, 16 * ks, G::SH, lane);
+      DSVG_MMA3(o[2 * np], ah, al, bh, bl, 0, 1);
+      DSVG_MMA3(o[2 * np + 1], ah, al, bh, bl, 2, 3);
+    }
+  }
+}
+template <int HD, int NT>
+__device__ __forceinline__ void gx3_mul_t(float (&o)[HD / 8][4], uint32_t z_tile, uint32_t y_tile, int w, int lane) {
+  using G = GAttn<HD, NT>;
+  constexpr uint32_t kLoH = G::kTileH * 2, kLoP = G::kTileP * 2;
+#pragma unroll
+  for (int nt = 0; nt < HD / 8; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[nt][e] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < NT; ++ks) {
+    uint32_t ah[4], al[4];
+    g_load_a_t(ah, z_tile, 16 * w, 16 * ks, G::SP, lane);
+    g_load_a_t(al, z_tile + kLoP, 16 * w, 16 * ks, G::SP, lane);
+#pragma unroll
+    for (int np = 0; np < HD / 16; ++np) {
+      uint32_t bh[4], bl[4];
+      g_load_b_kn(bh, y_tile, 16 * np, 16 * ks, G::SH, lane);
+      g_load_b_kn(bl, y_tile + kLoH, 16 * np, 16 * ks, G::SH, lane);
+      DSVG_MMA3(o[2 * np], ah, al, bh, bl, 0, 1);
+      DSVG_MMA3(o[2 * np + 1], ah, al, bh, bl, 2, 3);
+    }
+  }
+}
+template <int HD>
+__device__ __forceinline__ void gx3_store_global(bf16* dst, size_t lo_off, int ld, int L, int row0, const float (&c)[HD / 8][4],
+                                                 float mul, int g, int t) {
+#pragma unroll
+  for (int hrow = 0; hrow < 2; ++hrow) {
+    const int i = row0 + g + 8 * hrow;
+    if (i < L) {
+#pragma unroll
+      for (int nt = 0; nt < HD / 8; ++nt) {
+        const float x = c[nt][2 * hrow] * mul, y = c[nt][2 * hrow + 1] * mul;
+        const uint32_t hi = pack_bf16(x, y);
+        bf16* p = dst + size_t(i) * ld + 8 * nt + 2 * t;
+        *reinterpret_cast<uint32_t*>(p) = hi;
+        *reinterpret_cast<uint32_t*>(p + lo_off) = pack_lo(x, y, hi);
+      }
+    }
+  }
+}
+template <int NT>
+__device__ __forceinline__ void gx3_store_rows_smem(bf16* tile, int lo_elems, int st, int row0, const float (&c)[2 * NT][4],
+                                                    int g, int t) {
+#pragma unroll
+  for (int hrow = 0; hrow < 2; ++hrow) {
+    const int i = row0 + g + 8 * hrow;
+#pragma unroll
+    for (int nt = 0; nt < 2 * NT; ++nt) {
+      const uint32_t hi = pack_bf16(c[nt][2 * hrow], c[nt][2 * hrow + 1]);
+      bf16* p = tile + i * st + 8 * nt + 2 * t;
+      *reinterpret_cast<uint32_t*>(p) = hi;
+      *reinterpret_cast<uint32_t*>(p + lo_elems) = pack_lo(c[nt][2 * hrow], c[nt][2 * hrow + 1], hi);
+    }
+  }
+}
+
+template <int HD, int NT>
+__global__ void __launch_bounds__(32 * NT) attn_gx3_fwd_kernel(X3AttnArgs x) {
+  using G = GAttn<HD, NT>;
+  pdl_launch_dependents();
+  pdl_wait();
+  MmaAttnArgs& a = x.m;
+  drop_resolve(a.drop);
+  extern __shared__ __align__(16) bf16 sm_dyn[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int L = a.L, d = a.H * HD, ld = 3 * d;
+  bf16* Qs = sm_dyn;                   // hi, lo
+  bf16* Ks = Qs + 2 * G::kTileH;
+  bf16* Vs = Ks + 2 * G::kTileH;
+  uint8_t* kv = reinterpret_cast<uint8_t*>(Vs + 2 * G::kTileH);
+  const uint32_t q_t = smem_addr(Qs), k_t = smem_addr(Ks), v_t = smem_addr(Vs);
+  const long long npairs = (long long)a.nseq * a.H;
+  for (long long pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+    const int seq = int(pair / a.H), h = int(pair % a.H);
+    const size_t row0 = size_t(seq) * L;
+    const bf16* base = a.qkv + row0 * ld + h * HD;
+#pragma unroll
+    for (int pl = 0; pl < 2; ++pl) {
+      const bf16* b = base + (pl ? x.qkv_lo : 0);
+      g_stage<HD, NT>(Qs + pl * G::kTileH, b, ld, L);
+      g_stage<HD, NT>(Ks + pl * G::kTileH, b + d, ld, L);
+      g_stage<HD, NT>(Vs + pl * G::kTileH, b + 2 * d, ld, L);
+    }
+    cp_async_commit();
+    for (int j = threadIdx.x; j < G::LP; j += G::kThreads) kv[j] = (j < L && (a.valid == nullptr || a.valid[row0 + j] != 0)) ? 1 : 0;
+    cp_async_wait_all();
+    __syncthreads();
+    float s[2 * NT][4];
+    gx3_scores<HD, NT>(s, q_t, k_t, w, lane);
+    g_softmax<NT>(s, g_my_keys<NT>(kv, t), 16 * w, g, t, a.causal);
+    if (a.drop.p > 0.f) {
+      float mult[2 * NT][4];
+      g_dropout<NT>(mult, a.drop, (unsigned long long)pair, w, g, t);
+#pragma unroll
+      for (int nt = 0; nt < 2 * NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s[nt][e] *= mult[nt][e];
+    }
+    float o[HD / 8][4];
+    gx3_mul_regs<HD, NT>(o, s, v_t, lane);
+    gx3_store_global<HD>(a.out + row0 * d + h * HD, x.out_lo, d, L, 16 * w, o, 1.f, g, t);
+    __syncthreads();
+  }
+}
+
+template <int HD, int NT>
+__global__ void __launch_bounds__(32 * NT) attn_gx3_bwd_kernel(X3AttnArgs x) {
+  using G = GAttn<HD, NT>;
+  pdl_launch_dependents();
+  pdl_wait();
+  MmaAttnArgs& a = x.m;
+  drop_resolve(a.drop);
+  extern __shared__ __align__(16) bf16 sm_dyn[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int L = a.L, d = a.H * HD, ld = 3 * d;
+  bf16* Qs = sm_dyn;
+  bf16* Ks = Qs + 2 * G::kTileH;
+  bf16* Vs = Ks + 2 * G::kTileH;
+  bf16* Gs = Vs + 2 * G::kTileH;   // dO
+  bf16* Ps = Gs + 2 * G::kTileH;   // dropout-scaled probabilities  [query][key], hi then lo
+  bf16* Ds = Ps + 2 * G::kTileP;   // dS
+  uint8_t* kv = reinterpret_cast<uint8_t*>(Ds + 2 * G::kTileP);
+  const uint32_t q_t = smem_addr(Qs), k_t = smem_addr(Ks), v_t = smem_addr(Vs), g_t = smem_addr(Gs), p_t = smem_addr(Ps),
+                 d_t = smem_addr(Ds);
+  const long long npairs = (long long)a.nseq * a.H;
+  for (long long pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+    const int seq = int(pair / a.H), h = int(pair % a.H);
+    const size_t row0 = size_t(seq) * L;
+    const bf16* base = a.qkv + row0 * ld + h * HD;
+    const bf16* gbase = a.dout + row0 * d + h * HD;
+#pragma unroll
+    for (int pl = 0; pl < 2; ++pl) {
+      const bf16* b = base + (pl ? x.qkv_lo : 0);
+      g_stage<HD, NT>(Qs + pl * G::kTileH, b, ld, L);
+      g_stage<HD, NT>(Ks + pl * G::kTileH, b + d, ld, L);
+      g_stage<HD, NT>(Vs + pl * G::kTileH, b + 2 * d, ld, L);
+      g_stage<HD, NT>(Gs + pl * G::kTileH, gbase + (pl ? x.dout_lo : 0), d, L);
+    }
+    cp_async_commit();
+    for (int j = threadIdx.x; j < G::LP; j += G::kThreads) kv[j] = (j < L && (a.valid == nullptr || a.valid[row0 + j] != 0)) ? 1 : 0;
+    cp_async_wait_all();
+    __syncthreads();
+    float p[2 * NT][4], dp[2 * NT][4];
+    gx3_scores<HD, NT>(p, q_t, k_t, w, lane);
+    g_softmax<NT>(p, g_my_keys<NT>(kv, t), 16 * w, g, t, a.causal);
+    gx3_scores<HD, NT>(dp, g_t, v_t, w, lane);          // dP = dO . V^T
+    if (a.drop.p > 0.f) {
+      float mult[2 * NT][4];
+      g_dropout<NT>(mult, a.drop, (unsigned long long)pair, w, g, t);
+#pragma unroll
+      for (int nt = 0; nt < 2 * NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          dp[nt][e] *= mult[nt][e];
+          mult[nt][e] *= p[nt][e];
+        }
+      gx3_store_rows_smem<NT>(Ps, G::kTileP, G::SP, 16 * w, mult, g, t);
+    } else {
+      gx3_store_rows_smem<NT>(Ps, G::kTileP, G::SP, 16 * w, p, g, t);
+    }
+#pragma unroll
+    for (int hrow = 0; hrow < 2; ++hrow) {
+      float delta = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 2 * NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) delta = fmaf(dp[nt][2 * hrow + e], p[nt][2 * hrow + e], delta);
+      delta += __shfl_xor_sync(0xffffffffu, delta, 1);
+      delta += __shfl_xor_sync(0xffffffffu, delta, 2);
+#pragma unroll
+      for (int nt = 0; nt < 2 * NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) dp[nt][2 * hrow + e] = p[nt][2 * hrow + e] * (dp[nt][2 * hrow + e] - delta);
+    }
+    gx3_store_rows_smem<NT>(Ds, G::kTileP, G::SP, 16 * w, dp, g, t);
+    float o[HD / 8][4];
+    bf16* dbase = a.dqkv + row0 * ld + h * HD;
+    gx3_mul_regs<HD, NT>(o, dp, k_t, lane);                 // dQ rows of this warp = dS_w . K
+    gx3_store_global<HD>(dbase, x.dqkv_lo, ld, L, 16 * w, o, a.scale, g, t);
+    __syncthreads();                                        // every warp's rows of P and dS are in shared memory
+    gx3_mul_t<HD, NT>(o, d_t, q_t, w, lane);                // dK rows [16 w, +16) = dS^T . Q
+    gx3_store_global<HD>(dbase + d, x.dqkv_lo, ld, L, 16 * w, o, 1.f, g, t);
+    gx3_mul_t<HD, NT>(o, p_t, g_t, w, lane);                // dV rows = dropout(P)^T . dO
+    gx3_store_global<HD>(dbase + 2 * d, x.dqkv_lo, ld, L, 16 * w, o, 1.f, g, t);
+    __syncthreads();
+  }
+}
+
+template <int HD, int NT, bool BWD>
+static int launch_gx3_k(const X3AttnArgs& x, cudaStream_t st) {
+  using G = GAttn<HD, NT>;
+  const int smem = BWD ? GX3<HD, NT>::kSmemBwd : GX3<HD, NT>::kSmemFwd;
+  auto kern = [] {
+    if constexpr (BWD) return attn_gx3_bwd_kernel<HD, NT>;
+    else return attn_gx3_fwd_kernel<HD, NT>;
+  }();
+  static int per_sm = 0;
+  static bool configured[kMaxDevices] = {};
+  if (first_use_on_device(configured)) {
+    DSVG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int n = 0;
+    DSVG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, G::kThreads, size_t(smem)));
+    per_sm = n > 0 ? n : 1;
+  }
+  int sms = 148;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  const long long npairs = (long long)x.m.nseq * x.m.H;
+  long long blocks = (long long)sms * per_sm;
+  if (blocks > npairs) blocks = npairs;
+  DSVG_CUDA(launch_k(kern, dim3(int(blocks)), dim3(G::kThreads), size_t(smem), st, x));
+  ++g_launches;
+  return 0;
+}
+template <int HD>
+static int launch_gx3_nt(bool bwd, const X3AttnArgs& x, cudaStream_t st) {
+#define DSVG_GX3_CASE(NT) \
+  case NT: return bwd ? launch_gx3_k<HD, NT, true>(x, st) : launch_gx3_k<HD, NT, false>(x, st)
+  switch ((x.m.L + 15) / 16) {
+    DSVG_GX3_CASE(1);
+    DSVG_GX3_CASE(2);
+    DSVG_GX3_CASE(3);
+    DSVG_GX3_CASE(4);
+    DSVG_GX3_CASE(5);
+    default: DSVG_CHECK(false, "tensor-core attention: L = %d exceeds 80 positions", x.m.L);
+  }
+#undef DSVG_GX3_CASE
+}
+
 }  // namespace dsvg
 
 // head_dim 32 / 64, L <= 80, single-plane operands
@@ -1196,5 +1499,19 @@ int dsvg_attn_gmma(bool bwd, const bf16* qkv, const uint8_t* valid, bf16* out, c
   a.scale = q_scale; a.drop = drop; a.causal = causal;
   if (head_dim == 32) return launch_gmma_nt<32>(bwd, a, st);
   if (head_dim == 64) return launch_gmma_nt<64>(bwd, a, st);
+  DSVG_CHECK(false, "tensor-core attention: head_dim %d unsupported", head_dim);
+}
+
+// head_dim 32 / 64, L <= 80, two-plane (bf16x3) operands
+int dsvg_attn_gx3(bool bwd, const bf16* qkv, size_t qkv_lo, const uint8_t* valid, bf16* out, size_t out_lo, const bf16* dout,
+                  size_t dout_lo, bf16* dqkv, size_t dqkv_lo, int nseq, int L, int H, int head_dim, float q_scale, Dropout drop,
+                  int causal, cudaStream_t st) {
+  X3AttnArgs x{};
+  MmaAttnArgs& a = x.m;
+  a.qkv = qkv; a.valid = valid; a.out = out; a.dout = dout; a.dqkv = dqkv; a.nseq = nseq; a.L = L; a.H = H;
+  a.scale = q_scale; a.drop = drop; a.causal = causal;
+  x.qkv_lo = qkv_lo; x.out_lo = out_lo; x.dout_lo = dout_lo; x.dqkv_lo = dqkv_lo;
+  if (head_dim == 32) return launch_gx3_nt<32>(bwd, x, st);
+  if (head_dim == 64) return launch_gx3_nt<64>(bwd, x, st);
   DSVG_CHECK(false, "tensor-core attention: head_dim %d unsupported", head_dim);
 }

@@ -22,8 +22,8 @@ PROFILE = None
 
 
 class _Prof:
-    def __init__(self, family, flops, shape=None):
-        self.family, self.flops, self.shape = family, flops, shape
+    def __init__(self, family, flops, shape=None, nbytes=0.0):
+        self.family, self.flops, self.shape, self.nbytes = family, flops, shape, nbytes
 
     def __enter__(self):
         if PROFILE is not None:
@@ -35,7 +35,7 @@ class _Prof:
     def __exit__(self, *a):
         if PROFILE is not None:
             self.e1.record()
-            PROFILE.append((self.family, self.flops, self.e0, self.e1, self.shape))
+            PROFILE.append((self.family, self.flops, self.e0, self.e1, self.shape, self.nbytes))
         return False
 
 
@@ -102,14 +102,19 @@ def linear(X, W, M, N, K, *, bias=None, scale_cols=0, scale=1.0, relu=False, dro
         ep.out_f32, ep.out_f32_ld = out_f32.data_ptr(), out_f32.stride(0)
     if out_act is not None:
         ep.out_act, ep.out_lo_off, ep.out_act_ld = out_act.ptr, out_act.lo, out_act.ld
+    # algorithmic HBM bytes of this launch (operands read once, outputs written once)
+    nb = 2.0 * X.planes * M * K + 2.0 * W.planes * N * K
+    nb += (4.0 * M * N if residual is not None else 0) + (2.0 * M * N if mask is not None else 0)
+    nb += (4.0 * M * N if out_f32 is not None else 0) + (2.0 * out_act.planes * M * N if out_act is not None else 0)
     if ln is not None:
         gamma, beta, y, mean, rstd = ln
-        with _Prof("linear", 2.0 * M * N * K, (M, N, K)):
+        nb += 2.0 * y.planes * M * N + 8.0 * M
+        with _Prof("linear", 2.0 * M * N * K, (M, N, K), nb):
             rc = _lib.load().dsvg_linear_ln_fwd(X.ptr, X.lo, X.ld, W.ptr, W.lo, W.ld, M, N, K, C.byref(ep), gamma.data_ptr(),
                                                 beta.data_ptr(), y.ptr, mean.data_ptr(), rstd.data_ptr(), _stream())
         _lib.check(rc, "dsvg_linear_ln_fwd")
         return
-    with _Prof("linear", 2.0 * M * N * K, (M, N, K)):
+    with _Prof("linear", 2.0 * M * N * K, (M, N, K), nb):
         rc = _lib.load().dsvg_linear(X.ptr, X.lo, X.ld, W.ptr, W.lo, W.ld, M, N, K, C.byref(ep), _stream())
     _lib.check(rc, "dsvg_linear")
 
@@ -128,7 +133,7 @@ def linear_ln_bwd(dY, W, M, N, K, x, mean, rstd, gamma, *, dx_in=None, dx_out=No
 
 def outer(A, B, M, P, Q, Cout, *, alpha=1.0, alpha_dev=None, colsum=None):
     """Cout[P,Q] += alpha * A[M,P]^T . B[M,Q]; Cout fp32 (row stride = Cout.stride(0)); colsum[P] += alpha * sum_rows A."""
-    with _Prof("outer", 2.0 * M * P * Q, (M, P, Q)):
+    with _Prof("outer", 2.0 * M * P * Q, (M, P, Q), 2.0 * A.planes * M * P + 2.0 * B.planes * M * Q + 4.0 * P * Q):
         rc = _lib.load().dsvg_outer(A.ptr, A.lo, A.ld, B.ptr, B.lo, B.ld, M, P, Q, alpha, _p(alpha_dev),
                                     Cout.data_ptr(), Cout.stride(0), _p(colsum), _stream())
     _lib.check(rc, "dsvg_outer")
@@ -199,14 +204,14 @@ def ln_bwd(x, mean, rstd, gamma, M, D, *, dy=None, dz=None, valid=None, inv_cnt=
 
 
 def attn_fwd(qkv, key_valid, out, nseq, L, H, hd, drop, causal=False):
-    with _Prof("attn_fwd", 4.0 * nseq * L * L * H * hd):
+    with _Prof("attn_fwd", 4.0 * nseq * L * L * H * hd, None, 2.0 * qkv.planes * nseq * L * H * hd * 4):
         rc = _lib.load().dsvg_attn_fwd(qkv.ptr, qkv.lo, _p(key_valid), out.ptr, out.lo, nseq, L, H, hd, int(causal), drop[0],
                                        drop[1], drop[2], _stream())
     _lib.check(rc, "dsvg_attn_fwd")
 
 
 def attn_bwd(qkv, key_valid, dout, dqkv, nseq, L, H, hd, q_scale, drop, causal=False):
-    with _Prof("attn_bwd", 8.0 * nseq * L * L * H * hd):
+    with _Prof("attn_bwd", 8.0 * nseq * L * L * H * hd, None, 2.0 * qkv.planes * nseq * L * H * hd * 7):
         rc = _lib.load().dsvg_attn_bwd(qkv.ptr, qkv.lo, _p(key_valid), dout.ptr, dout.lo, dqkv.ptr, dqkv.lo, nseq, L, H,
                                        hd, int(causal), q_scale, drop[0], drop[1], drop[2], _stream())
     _lib.check(rc, "dsvg_attn_bwd")
