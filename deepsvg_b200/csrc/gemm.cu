@@ -484,6 +484,14 @@ __device__ __forceinline__ void epilogue_chunk_lean(uint32_t (&v)[32], uint32_t 
           u.x = *reinterpret_cast<uint32_t*>(&h0);
           u.y = *reinterpret_cast<uint32_t*>(&h1);
           *reinterpret_cast<uint2*>(outa_p + size_t(4 * it) * ep.out_act_ld) = u;
+          if (ep.out_lo_off != 0) {   // parity mode: lo plane = bf16(v - hi)  (warp-uniform branch)
+            const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+            h0 = __floats2bfloat162_rn(x.x - f0.x, x.y - f0.y);
+            h1 = __floats2bfloat162_rn(x.z - f1.x, x.w - f1.y);
+            u.x = *reinterpret_cast<uint32_t*>(&h0);
+            u.y = *reinterpret_cast<uint32_t*>(&h1);
+            *reinterpret_cast<uint2*>(outa_p + ep.out_lo_off + size_t(4 * it) * ep.out_act_ld) = u;
+          }
         }
       }
     }
@@ -640,7 +648,11 @@ __host__ __device__ constexpr int lin_epi_warps(int mode, int bn) {
   return ((mode >= 3 && mode <= 9 && mode != 6) && bn == 256) ? 16 : 8;
 }
 // act-output lean modes write their bf16 tile through shared memory with one TMA store per 64-column box
-__host__ __device__ constexpr bool lin_tma_out(int mode) { return mode == 1 || mode == 2 || mode == 3 || mode == 5; }
+// (single-plane tensors only: the two-plane parity mode sends the same feature sets through the per-warp staged epilogue,
+// which writes the hi and lo planes with plain vector stores)
+__host__ __device__ constexpr bool lin_tma_out(int mode, int nplanes = 1) {
+  return nplanes == 1 && (mode == 1 || mode == 2 || mode == 3 || mode == 5);
+}
 
 __device__ __forceinline__ void trace_stamp(const Epi& ep, int it, int slot, int lane) {
   if (ep.dbg != nullptr && blockIdx.x == 0 && lane == 0 && it < 16) ep.dbg[it * 16 + slot] = clock64();
@@ -653,7 +665,7 @@ struct LinearCfg {
   static constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB
   static constexpr int kBBytes = BN * kBlockK * 2;       // 16/32 KB
   static constexpr int kStageBytes = NPLANES * (kABytes + kBBytes);
-  static constexpr int kStagingBytes = lin_tma_out(MODE) ? BN * kBlockM * 2 : kEpiWarps * kStageWarpBytes;
+  static constexpr int kStagingBytes = lin_tma_out(MODE, NPLANES) ? BN * kBlockM * 2 : kEpiWarps * kStageWarpBytes;
   // BN = 128 single-plane kernels are sized so that TWO CTAs fit one SM (2 x 256 TMEM columns, <= 113 KB of shared
   // memory and <= 102 registers each): twice the TMA loads in flight and twice the epilogue warps per SM.
   static constexpr int kCtasPerSm = (BN == 128 && NPLANES == 1) ? 2 : 1;
@@ -845,7 +857,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           tmem_ld_wait();
           plain_rows_chunk(v, stage_buf, lane, row0, n0 + c, M, N, ep);
         }
-      } else if constexpr (lin_tma_out(MODE)) {
+      } else if constexpr (lin_tma_out(MODE, NPLANES)) {
         // Streamed TMA-store epilogue.  A "pass" = all epilogue warps draining kCols accumulator columns into their
         // 64-column boxes of the staging tile; each pass ends with ONE named barrier after which an elected thread
         // bulk-stores the pass's boxes as one group.  Box reuse: the boxes of pass ci were last stored kPasses groups
@@ -1278,7 +1290,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       if (warp == 2) trace_stamp(ep, it, 11, lane);
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
-    if constexpr (lin_tma_out(MODE)) {
+    if constexpr (lin_tma_out(MODE, NPLANES)) {
       if (warp == 2 && lane == 0) tma_store_wait_all();   // bulk stores must complete before the CTA's smem goes away
     }
     if constexpr (MODE == 9) {
@@ -1526,7 +1538,7 @@ template <int BN, int NPLANES, int MODE>
 static int launch_linear_mode(const CUtensorMap& a, const CUtensorMap& alo, const CUtensorMap& b, const CUtensorMap& blo,
                               int M, int N, int K, const Epi& ep, cudaStream_t st) {
   CUtensorMap c = a, mk = a;
-  if (lin_tma_out(MODE)) {
+  if (lin_tma_out(MODE, NPLANES)) {
     if (make_map(&c, ep.out_act, N, M, ep.out_act_ld, 64, 128)) return 1;
     if (ep.mask != nullptr && make_map(&mk, ep.mask, N, M, ep.mask_ld, 64, 128)) return 1;
   }
@@ -1559,17 +1571,33 @@ static int launch_linear_fast(const CUtensorMap& a, const CUtensorMap& b, int M,
   }
 }
 
+// parity mode (two bf16 planes per operand, 128-wide tiles): the same lean feature sets, staged per-warp epilogue
+static int launch_linear_split(const CUtensorMap& a, const CUtensorMap& alo, const CUtensorMap& b, const CUtensorMap& blo, int M,
+                               int N, int K, const Epi& ep, cudaStream_t st) {
+  switch (ep.mode) {
+    case 1: return launch_linear_mode<128, 2, 1>(a, alo, b, blo, M, N, K, ep, st);
+    case 2: return launch_linear_mode<128, 2, 2>(a, alo, b, blo, M, N, K, ep, st);
+    case 3: return launch_linear_mode<128, 2, 3>(a, alo, b, blo, M, N, K, ep, st);
+    case 4: return launch_linear_mode<128, 2, 4>(a, alo, b, blo, M, N, K, ep, st);
+    case 5: return launch_linear_mode<128, 2, 5>(a, alo, b, blo, M, N, K, ep, st);
+    case 6: return launch_linear_mode<128, 2, 6>(a, alo, b, blo, M, N, K, ep, st);
+    case 7: return launch_linear_mode<128, 2, 7>(a, alo, b, blo, M, N, K, ep, st);
+    default: return launch_linear_mode<128, 2, 0>(a, alo, b, blo, M, N, K, ep, st);
+  }
+}
+
 // which lean epilogue (if any) covers exactly the requested steps
 static int pick_mode(const Epi& ep, bool split, int N) {
   static const bool off = [] { const char* e = getenv("DSVG_EPI"); return e && e[0] == 'g'; }();  // "generic"
-  if (off || split) return 0;
+  if (off) return 0;
   if (ep.vec == 0) {   // unaligned rows: only the plain "acc + bias -> fp32" head epilogue has a lean version
     static const bool no7 = [] { const char* e = getenv("DSVG_EPI"); return e && e[0] == '7'; }();  // A/B switch
     const bool plain = ep.out_f32 && !ep.out_act && !ep.acc_scale_dev && ep.scale_cols == 0 && !ep.relu &&
                        !(ep.drop.p > 0.f) && !ep.rowvec && !ep.mask && !ep.residual;
     return (plain && !no7) ? 7 : 0;
   }
-  if (ep.vec != 1 || ep.mask_lo_off != 0 || ep.out_lo_off != 0) return 0;
+  if (ep.vec != 1) return 0;
+  if (!split && (ep.mask_lo_off != 0 || ep.out_lo_off != 0)) return 0;   // single-plane operands with two-plane outputs: generic
   uint32_t f = 0;
   if (ep.acc_scale_dev) f |= F_ACCS;
   if (ep.bias) f |= F_BIAS;
@@ -1588,7 +1616,7 @@ static int pick_mode(const Epi& ep, bool split, int N) {
     // mode 4 also bias and residual, so that it covers the latent / group-level "global" linears and their dgrads
     const uint32_t optional = have & (F_DROP | F_ROWVEC | ((have & F_OUTF) && !(have & F_ACCS) ? (F_BIAS | F_RES) : 0u));
     if ((f & ~optional) == (have & ~optional) && (f & ~have) == 0) {
-      if (lin_tma_out(k + 1)) {
+      if (lin_tma_out(k + 1, split ? 2 : 1)) {
         const bool ok = N % 8 == 0 && ep.out_act_ld % 8 == 0 && ep.scale_cols % 32 == 0 && (reinterpret_cast<uintptr_t>(ep.out_act) & 15) == 0 &&
                         (!ep.mask || (ep.mask_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(ep.mask) & 15) == 0)) &&
                         (!ep.bias || (reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0);
@@ -1708,7 +1736,7 @@ extern "C" int dsvg_linear(const dsvg_bf16* X, size_t x_lo_off, int lda, const d
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ep.mode = pick_mode(ep, split, N);
-  if (split) return launch_linear_mode<128, 2, 0>(a, alo, b, blo, M, N, K, ep, st);
+  if (split) return launch_linear_split(a, alo, b, blo, M, N, K, ep, st);
   return wide ? launch_linear_fast<256>(a, b, M, N, K, ep, st) : launch_linear_fast<128>(a, b, M, N, K, ep, st);
 }
 

@@ -22,4 +22,12 @@ done
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:outer_kernel -s 2 -c 1 -o gpurun_out/${R}_mode_outer -f python tools/prof_mode.py outer > /dev/null 2>&1
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:attn_mma -s 2 -c 2 -o gpurun_out/${R}_mode_attn -f python tools/prof_mode.py attn > /dev/null 2>&1
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:ln_bwd -s 1 -c 1 -o gpurun_out/${R}_mode_ln_bwd -f python tools/prof_mode.py ln_bwd > /dev/null 2>&1
+# parity mode (bf16x3): launch list of one step, one capture per linear role at the path-level shape, the attention kernels
+DSVG_PRECISION=bf16x3 DSVG_GRAPHS=0 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${R}_x3_launches.csv \
+    python tools/one_step.py 512 2 hier > gpurun_out/${R}_x3_one_step.log 2>&1
+for m in qkv ffn1 proj; do
+  DSVG_PLANES=2 timeout 200 ncu --set full --clock-control none --import-source on -k regex:linear_kernel -s 2 -c 1 \
+      -o gpurun_out/${R}_x3mode_${m} -f python tools/prof_mode.py ${m} > /dev/null 2>&1
+done
+DSVG_PLANES=2 timeout 200 ncu --set full --clock-control none --import-source on -k regex:attn_x3 -s 2 -c 2 -o gpurun_out/${R}_x3mode_attn -f python tools/prof_mode.py attn > /dev/null 2>&1
 ls gpurun_out | grep ${R}_ | wc -l

@@ -9,22 +9,26 @@ from deepsvg_b200 import ops
 dev = torch.device("cuda:0")
 which = sys.argv[1]
 M = 131072
+PL = int(os.environ.get("DSVG_PLANES", "1"))     # 2: parity-mode (bf16x3) operands for the linear roles
 
 
 def go(M, N, K, **kw):
-    X = ops.Act(M, K, 1, dev, zero=True)
+    X = ops.Act(M, K, PL, dev, zero=True)
     X.t.normal_()
-    W = ops.Act(N, K, 1, dev, zero=True)
+    W = ops.Act(N, K, PL, dev, zero=True)
     W.t.normal_(std=K ** -0.5)
+    if PL == 2:
+        X.t[1] *= 2.0 ** -9
+        W.t[1] *= 2.0 ** -9
     for _ in range(4):
         ops.linear(X, W, M, N, K, **kw)
     torch.cuda.synchronize()
 
 
 if which == "ffn1":
-    go(M, 512, 256, bias=torch.zeros(512, device=dev), relu=True, drop=(0.1, 3, 7), out_act=ops.Act(M, 512, 1, dev))
+    go(M, 512, 256, bias=torch.zeros(512, device=dev), relu=True, drop=(0.1, 3, 7), out_act=ops.Act(M, 512, PL, dev))
 elif which == "qkv":
-    go(M, 768, 256, bias=torch.zeros(768, device=dev), scale_cols=256, scale=0.17, out_act=ops.Act(M, 768, 1, dev))
+    go(M, 768, 256, bias=torch.zeros(768, device=dev), scale_cols=256, scale=0.17, out_act=ops.Act(M, 768, PL, dev))
 elif which == "proj":
     x = torch.zeros(M, 256, device=dev)
     go(M, 256, 256, bias=torch.zeros(256, device=dev), drop=(0.1, 4, 7), residual=x, out_f32=x)
@@ -68,9 +72,9 @@ elif which == "outer":
     torch.cuda.synchronize()
 elif which == "attn":
     nseq, L, H, hd = 4096, 32, 8, 32
-    qkv = ops.Act(M, 768, 1, dev, zero=True)
+    qkv = ops.Act(M, 768, PL, dev, zero=True)
     qkv.t.normal_(std=0.5)
-    o, do, dq = ops.Act(M, 256, 1, dev), ops.Act(M, 256, 1, dev, zero=True), ops.Act(M, 768, 1, dev)
+    o, do, dq = ops.Act(M, 256, PL, dev), ops.Act(M, 256, PL, dev, zero=True), ops.Act(M, 768, PL, dev)
     for _ in range(3):
         ops.attn_fwd(qkv, None, o, nseq, L, H, hd, (0.1, 2, 9))
         ops.attn_bwd(qkv, None, do, dq, nseq, L, H, hd, 0.17, (0.1, 2, 9))
@@ -78,9 +82,9 @@ elif which == "attn":
 elif which == "gattn":        # general tensor-core attention at the scaled config's path-level shape
     nseq, L, H, hd = 2048, 66, 8, 64
     Mg = nseq * L
-    qkv = ops.Act(Mg, 1536, 1, dev, zero=True)
+    qkv = ops.Act(Mg, 1536, PL, dev, zero=True)
     qkv.t.normal_(std=0.5)
-    o, do, dq = ops.Act(Mg, 512, 1, dev), ops.Act(Mg, 512, 1, dev, zero=True), ops.Act(Mg, 1536, 1, dev)
+    o, do, dq = ops.Act(Mg, 512, PL, dev), ops.Act(Mg, 512, PL, dev, zero=True), ops.Act(Mg, 1536, PL, dev)
     for _ in range(3):
         ops.attn_fwd(qkv, None, o, nseq, L, H, hd, (0.1, 2, 9))
         ops.attn_bwd(qkv, None, do, dq, nseq, L, H, hd, 0.125, (0.1, 2, 9))

@@ -111,6 +111,24 @@ def main():
             f.write("# ncu --set full --clock-control none, selected raw metrics per captured launch (%s)\n" % rep)
             for d in ncu_raw(rep):
                 f.write(json.dumps(d) + "\n")
+    # parity mode (bf16x3): launch shares of one step + the captured roles
+    if os.path.exists(g + "x3_launches.csv"):
+        data, agg = launches(g + "x3_launches.csv", n_per_step)
+        tot = sum(a[1] for a in agg.values())
+        with open("%s/%s_x3_launch_shares.txt" % (OUT, R), "w") as f:
+            f.write("# one PARITY-MODE (bf16x3) train step (N=512, eager launches) under `ncu --metrics gpu__time_duration.sum "
+                    "--clock-control none`: last %d launches.  total %.0f us\n" % (len(data), tot))
+            for k, a in sorted(agg.items(), key=lambda x: -x[1][1]):
+                f.write("%9.0f us %5.1f%% %4d  %s\n" % (a[1], 100 * a[1] / tot, a[0], k))
+    with open("%s/%s_x3_ncu.txt" % (OUT, R), "w") as f:
+        f.write("# ncu --set full --clock-control none: parity-mode (two bf16 planes, three products) kernels at the path-level "
+                "shape (DSVG_PLANES=2 tools/prof_mode.py)\n")
+        for name in ("qkv", "ffn1", "proj", "attn"):
+            rep = g + "x3mode_%s.ncu-rep" % name
+            if os.path.exists(rep):
+                for d in ncu_raw(rep):
+                    d["role"] = name
+                    f.write(json.dumps(d) + "\n")
     print("wrote", sorted(x for x in os.listdir(OUT) if x.startswith(R)))
 
 
