@@ -6,6 +6,7 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv > gpurun_out/${R}_nvidia_smi.csv
 timeout 900 python -m pytest tests -m gpu -q --no-header 2>&1 | tail -12 > gpurun_out/${R}_pytest_gpu.txt
 tail -3 gpurun_out/${R}_pytest_gpu.txt
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${R}_smoke.txt 2>&1; tail -2 gpurun_out/${R}_smoke.txt
 timeout 600 python bench.py 2> gpurun_out/${R}_bench_stderr.log | tail -1 > gpurun_out/${R}_bench_n1.json
 timeout 400 python bench.py --impl reference --steps 5 --warmup 1 2>/dev/null | tail -1 > gpurun_out/${R}_bench_reference.json
 timeout 500 python bench.py --config fonts --steps 20 2>/dev/null | tail -1 > gpurun_out/${R}_bench_fonts.json
@@ -30,4 +31,13 @@ for m in qkv ffn1 proj; do
       -o gpurun_out/${R}_x3mode_${m} -f python tools/prof_mode.py ${m} > /dev/null 2>&1
 done
 DSVG_PLANES=2 timeout 200 ncu --set full --clock-control none --import-source on -k regex:attn_x3 -s 2 -c 2 -o gpurun_out/${R}_x3mode_attn -f python tools/prof_mode.py attn > /dev/null 2>&1
+# gpurun copies back at most 64 MiB: keep the raw-metric CSV of every capture, and the full reports (with source) of three kernels
+for rep in gpurun_out/${R}_*.ncu-rep; do
+  ncu -i $rep --page raw --csv > ${rep%.ncu-rep}.raw.csv 2>/dev/null
+  case $rep in
+    *_mode_qkv.ncu-rep|*_mode_lnfwd.ncu-rep|*_x3mode_qkv.ncu-rep) ;;
+    *) rm -f $rep ;;
+  esac
+done
 ls gpurun_out | grep ${R}_ | wc -l
+du -sh gpurun_out

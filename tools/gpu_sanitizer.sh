@@ -28,4 +28,24 @@ for _ in range(2):
 torch.cuda.synchronize()
 print("train steps ok, loss", ls["loss"].item())
 PY
-tail -12 $OUT
+echo "== compute-sanitizer --tool memcheck : parity-mode (bf16x3) train steps: head_dim 32 / L 12 (attn_x3) and head_dim 64 / L 42 (attn_gx3), lean two-plane epilogues, dropout" >> $OUT
+DSVG_GRAPHS=0 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 3 python - >> $OUT 2>&1 <<'PY'
+import torch
+from oracle import svg_oracle as O
+from deepsvg_b200 import Hierarchical, SVGLoss, SVGTransformer
+W = {"kl_tolerance": 0.1, "loss_kl_weight": 1.0, "loss_cmd_weight": 1.0, "loss_args_weight": 2.0, "loss_visibility_weight": 1.0}
+for heads, seq in ((4, 10), (2, 40)):
+    small = dict(d_model=128, n_heads=heads, dim_feedforward=256, dim_z=64, n_layers=2, n_layers_decode=2, max_num_groups=4, max_seq_len=seq)
+    cfg = Hierarchical(use_vae=True, **small)
+    m = SVGTransformer(cfg, precision="bf16x3").cuda().train()
+    lf = SVGLoss(cfg).cuda()
+    c, a = O.synth_batch(O.make_cfg("hierarchical", **small), 6, seed=1)
+    c, a = c.cuda(), a.cuda()
+    for _ in range(2):
+        m.zero_grad(set_to_none=True)
+        ls = lf(m(c, a, c, a, params={}), None, weights=W)
+        ls["loss"].backward()
+    torch.cuda.synchronize()
+    print("bf16x3 train steps ok (heads %d, seq %d), loss" % (heads, seq), ls["loss"].item())
+PY
+tail -16 $OUT

@@ -42,7 +42,13 @@ WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__registers_per_th
 
 
 def ncu_raw(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    """rep: path of the .ncu-rep; the GPU-side script leaves `<rep minus .ncu-rep>.raw.csv` (ncu --page raw --csv) next to it
+    and deletes most reports (64 MiB copy-back limit), so the CSV is preferred."""
+    pre = rep[:-len(".ncu-rep")] + ".raw.csv"
+    if os.path.exists(pre):
+        out = open(pre, errors="ignore").read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     if len(rows) < 3:
         return []
@@ -93,7 +99,7 @@ def main():
                 "dsvg::linear_kernel at the path-level shape (tools/prof_mode.py), selected raw metrics\n")
         for name, (mode, what) in MODES.items():
             rep = g + "mode_%s.ncu-rep" % name
-            if not os.path.exists(rep):
+            if not (os.path.exists(rep) or os.path.exists(rep[:-8] + ".raw.csv")):
                 continue
             for d in ncu_raw(rep)[:1]:
                 d["role"], d["mode"] = what, mode
@@ -105,7 +111,7 @@ def main():
     json.dump(per_mode, open("%s/%s_linear_modes.json" % (OUT, R), "w"), indent=1)
     for name in ("outer", "attn", "ln_bwd"):
         rep = g + "mode_%s.ncu-rep" % name
-        if not os.path.exists(rep):
+        if not (os.path.exists(rep) or os.path.exists(rep[:-8] + ".raw.csv")):
             continue
         with open("%s/%s_ncu_%s.txt" % (OUT, R, name), "w") as f:
             f.write("# ncu --set full --clock-control none, selected raw metrics per captured launch (%s)\n" % rep)
@@ -125,7 +131,7 @@ def main():
                 "shape (DSVG_PLANES=2 tools/prof_mode.py)\n")
         for name in ("qkv", "ffn1", "proj", "attn"):
             rep = g + "x3mode_%s.ncu-rep" % name
-            if os.path.exists(rep):
+            if os.path.exists(rep) or os.path.exists(rep[:-8] + ".raw.csv"):
                 for d in ncu_raw(rep):
                     d["role"] = name
                     f.write(json.dumps(d) + "\n")
