@@ -1343,14 +1343,21 @@ __device__ __forceinline__ void outer_chunk_vec(uint32_t (&v)[32], uint32_t stag
 // ------------------------------------------------------------------------------------------------
 // dsvg_outer kernel (MN-major operands): one output tile [128 x BQ] per CTA, contraction over an M range
 // ------------------------------------------------------------------------------------------------
-template <int BQ, int NPLANES>
+// BP = 256 ("tall" tile, fast mode, BQ = 256): two [128 x 256] accumulators fill all 512 TMEM columns and share every B
+// stage, so a CTA ingests 64 KB per 64-row block for 256 x 256 outputs instead of 48 KB for 128 x 256 -- a third less
+// through the SM's L2 port, which is what bounds this kernel (profiles/README.md: 604 MB at 10.1 TB/s for 268 MB of
+// operands).  No TMEM is left for the ones-MMA: the column sums (bias gradient) are accumulated by the epilogue warps, which
+// are idle during the main loop, straight from the A tiles in shared memory.
+template <int BQ, int NPLANES, int BP = 128>
 struct OuterCfg {
+  static_assert(BP == 128 || (BP == 256 && BQ == 256 && NPLANES == 1), "outer: tall tiles are single-plane 256 x 256 only");
   static constexpr int kBoxBytes = 64 * 64 * 2;                 // [64 rows(m) x 64 cols] = 8 KB
-  static constexpr int kABytes = 2 * kBoxBytes;                 // 128 P columns
+  static constexpr int kABytes = (BP / 64) * kBoxBytes;         // BP P columns
   static constexpr int kBBytes = (BQ / 64) * kBoxBytes;         // BQ Q columns
   static constexpr int kStageBytes = NPLANES * (kABytes + kBBytes);
-  static constexpr int kStages = (NPLANES == 1) ? 4 : 2;
-  static constexpr int kTmemCols = 2 * BQ;  // BQ accumulator columns + 64 for the column-sum (bias) tile, power of 2
+  static constexpr int kStages = (NPLANES == 1) ? (BP == 256 ? 3 : 4) : 2;
+  // BP = 128: BQ accumulator columns + 64 for the column-sum (bias) tile, power of 2; BP = 256: two accumulators
+  static constexpr int kTmemCols = 2 * BQ;
   static constexpr int kOnesBytes = 4096;   // 16 K-rows x 128 B of bf16 1.0 (B operand of the column-sum MMA) + slack
   // 8 epilogue warps (two per TMEM lane quarter, each draining half of the BQ columns).  Their transposition buffers
   // alias the operand stages: when the accumulator barrier fires every TMA load has landed and every MMA has retired.
@@ -1361,17 +1368,21 @@ struct OuterCfg {
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kOnesBytes + kStagingBytes + 256;
 };
 
-template <int BQ, int NPLANES>
-__global__ void __launch_bounds__((OuterCfg<BQ, NPLANES>::kThreads), 1)
+template <int BQ, int NPLANES, int BP = 128>
+__global__ void __launch_bounds__((OuterCfg<BQ, NPLANES, BP>::kThreads), 1)
 outer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
              const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo, int M, int P, int Q,
              int mblk_per_split, float alpha, const float* alpha_dev, float* C, int ldc, float* colsum_out,
              uint32_t lbo, uint32_t sbo, int vec) {
-  using Cfg = OuterCfg<BQ, NPLANES>;
+  using Cfg = OuterCfg<BQ, NPLANES, BP>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* tiles = smem;
   uint8_t* ones = smem + Cfg::kStages * Cfg::kStageBytes;  // 1024-aligned
+  const int q_tiles = (Q + BQ - 1) / BQ;
+  const bool do_colsum = colsum_out != nullptr && (blockIdx.x % q_tiles) == 0;
+  // tall tiles: the epilogue warps read every A stage too (column sums) and release it together with the MMA commit
+  const bool smem_colsum = BP == 256 && do_colsum;
   float* staging = reinterpret_cast<float*>(tiles);   // epilogue only, after the main loop (see OuterCfg)
   uint64_t* bars = reinterpret_cast<uint64_t*>(ones + Cfg::kOnesBytes + Cfg::kStagingBytes);
   uint64_t* full_bar = bars;
@@ -1387,7 +1398,7 @@ outer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], smem_colsum ? 1 + Cfg::kEpiWarps : 1);
     }
     mbar_init(tfull_bar, 1);
     fence_barrier_init();
@@ -1406,9 +1417,7 @@ outer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();   // everything above touched only this CTA's shared memory / TMEM
 
-  const int q_tiles = (Q + BQ - 1) / BQ;
-  const bool do_colsum = colsum_out != nullptr && (blockIdx.x % q_tiles) == 0;
-  const int p0 = (blockIdx.x / q_tiles) * 128;
+  const int p0 = (blockIdx.x / q_tiles) * BP;
   const int q0 = (blockIdx.x % q_tiles) * BQ;
   const int total_mblk = (M + 63) / 64;
   const int mb_begin = blockIdx.y * mblk_per_split;
@@ -1424,7 +1433,7 @@ outer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         uint8_t* st = tiles + stage * Cfg::kStageBytes;
         mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
 #pragma unroll
-        for (int i = 0; i < 2; ++i) tma_load_2d(st + i * Cfg::kBoxBytes, &tmA, &full_bar[stage], p0 + 64 * i, mb * 64);
+        for (int i = 0; i < BP / 64; ++i) tma_load_2d(st + i * Cfg::kBoxBytes, &tmA, &full_bar[stage], p0 + 64 * i, mb * 64);
 #pragma unroll
         for (int j = 0; j < BQ / 64; ++j)
           tma_load_2d(st + Cfg::kABytes + j * Cfg::kBoxBytes, &tmB, &full_bar[stage], q0 + 64 * j, mb * 64);
@@ -1459,9 +1468,13 @@ outer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const uint32_t a_lo = b_hi + Cfg::kBBytes;
         const uint32_t b_lo = a_lo + Cfg::kABytes;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)  // 16 rows (= 2 KB) of the 64-row block per UMMA
+        for (int k = 0; k < 4; ++k) {  // 16 rows (= 2 KB) of the 64-row block per UMMA
           umma_f16(tmem_base, umma_smem_desc(a_hi + k * 2048, lbo, sbo), umma_smem_desc(b_hi + k * 2048, lbo, sbo), idesc,
                    (i | k) != 0 ? 1u : 0u);
+          if constexpr (BP == 256)   // second accumulator: P columns [128, 256) of the tile against the same B rows
+            umma_f16(tmem_base + BQ, umma_smem_desc(a_hi + 2 * Cfg::kBoxBytes + k * 2048, lbo, sbo),
+                     umma_smem_desc(b_hi + k * 2048, lbo, sbo), idesc, (i | k) != 0 ? 1u : 0u);
+        }
         if (NPLANES == 2) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
@@ -1470,7 +1483,7 @@ outer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           for (int k = 0; k < 4; ++k)
             umma_f16(tmem_base, umma_smem_desc(a_lo + k * 2048, lbo, sbo), umma_smem_desc(b_hi + k * 2048, lbo, sbo), idesc, 1u);
         }
-        if (do_colsum) {
+        if (BP == 128 && do_colsum) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             umma_f16(tmem_base + BQ, umma_smem_desc(a_hi + k * 2048, lbo, sbo), umma_smem_desc(ones_addr, lbo, sbo), idesc1,
@@ -1493,19 +1506,68 @@ outer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int half = (warp - 2) >> 2;      // which half of the BQ accumulator columns this warp drains
     const uint32_t stage_buf = smem_u32(staging) + (warp - 2) * kStageWarpBytes;
     if (alpha_dev != nullptr) alpha *= __ldg(alpha_dev);
+    const int ew = warp - 2;
+    float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if constexpr (BP == 256) {
+      if (smem_colsum) {
+        // warp ew owns rows ew, ew + 8, ... of every 64-row block; lane l owns the 16-byte chunk of P columns [8 l, 8 l + 8)
+        // (box l >> 3, chunk l & 7, stored at chunk ^ (row & 7) by the 128-byte swizzle; row & 7 == ew for all of this warp's rows)
+        int stage = 0;
+        uint32_t phase = 0;
+        const uint32_t off = uint32_t(lane >> 3) * Cfg::kBoxBytes + uint32_t(ew) * 128u + (uint32_t((lane & 7) ^ ew) << 4);
+        for (int i = 0; i < num_mb; ++i) {
+          mbar_wait(&full_bar[stage], phase);
+          const uint8_t* at = tiles + stage * Cfg::kStageBytes + off;
+#pragma unroll
+          for (int rr = 0; rr < 8; ++rr) {
+            const uint4 u = *reinterpret_cast<const uint4*>(at + rr * 1024);
+            const float4 lo4 = bf16x4_to_f4(make_uint2(u.x, u.y)), hi4 = bf16x4_to_f4(make_uint2(u.z, u.w));
+            cs[0] += lo4.x; cs[1] += lo4.y; cs[2] += lo4.z; cs[3] += lo4.w;
+            cs[4] += hi4.x; cs[5] += hi4.y; cs[6] += hi4.z; cs[7] += hi4.w;
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty_bar[stage]);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        // the transposition buffers below alias stage 0: no warp may start draining while another still reads an A tile
+        named_bar_sync(3, Cfg::kEpiWarps * 32);
+      }
+    }
     mbar_wait(tfull_bar, 0);
     tc_fence_after();
     Epi dummy{};
 #pragma unroll 1
-    for (int c = half * (BQ / 2); c < (half + 1) * (BQ / 2); c += 32) {
-      if (q0 + c >= Q) break;
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(c), v);
-      tmem_ld_wait();
-      if (vec) outer_chunk_vec(v, stage_buf, lane, p0 + quarter * 32, q0 + c, P, Q, alpha, C, ldc);
-      else epilogue_chunk<true>(v, stage_buf, lane, (long long)p0 + quarter * 32, q0 + c, P, Q, dummy, alpha, C, ldc);
+    for (int pa = 0; pa < BP / 128; ++pa) {
+      const int pr0 = p0 + 128 * pa + quarter * 32;
+      if (p0 + 128 * pa >= P) break;
+#pragma unroll 1
+      for (int c = half * (BQ / 2); c < (half + 1) * (BQ / 2); c += 32) {
+        if (q0 + c >= Q) break;
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(pa * BQ + c), v);
+        tmem_ld_wait();
+        if (vec) outer_chunk_vec(v, stage_buf, lane, pr0, q0 + c, P, Q, alpha, C, ldc);
+        else epilogue_chunk<true>(v, stage_buf, lane, (long long)pr0, q0 + c, P, Q, dummy, alpha, C, ldc);
+      }
     }
-    if (do_colsum && half == 0) {  // column 0 of the [128 x 64] tile = sum over this CTA's rows of A[:, p]
+    if constexpr (BP == 256) {
+      if (smem_colsum) {
+        // cross-warp reduction of the column sums through the B half of stage 0 (the transposition buffers use < 40 KB)
+        float* scr = reinterpret_cast<float*>(tiles + 40960);
+        *reinterpret_cast<float4*>(scr + ew * 256 + lane * 8) = make_float4(cs[0], cs[1], cs[2], cs[3]);
+        *reinterpret_cast<float4*>(scr + ew * 256 + lane * 8 + 4) = make_float4(cs[4], cs[5], cs[6], cs[7]);
+        named_bar_sync(3, Cfg::kEpiWarps * 32);
+        const int j = threadIdx.x - 64;
+        float sum = 0.f;
+#pragma unroll
+        for (int w2 = 0; w2 < Cfg::kEpiWarps; ++w2) sum += scr[w2 * 256 + j];
+        if (p0 + j < P) atomicAdd(colsum_out + p0 + j, sum * alpha);
+      }
+    }
+    if (BP == 128 && do_colsum && half == 0) {  // column 0 of the [128 x 64] tile = sum over this CTA's rows of A[:, p]
       uint32_t v[32];
       tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(BQ), v);
       tmem_ld_wait();
@@ -1628,17 +1690,17 @@ static int pick_mode(const Epi& ep, bool split, int N) {
   return 0;
 }
 
-template <int BQ, int NPLANES>
+template <int BQ, int NPLANES, int BP = 128>
 static int launch_outer(const CUtensorMap& a, const CUtensorMap& alo, const CUtensorMap& b, const CUtensorMap& blo,
                         int M, int P, int Q, float alpha, const float* alpha_dev, float* C, int ldc, float* colsum_out,
                         cudaStream_t st) {
-  using Cfg = OuterCfg<BQ, NPLANES>;
+  using Cfg = OuterCfg<BQ, NPLANES, BP>;
   static bool configured[kMaxDevices] = {};
   if (first_use_on_device(configured)) {
-    DSVG_CUDA(cudaFuncSetAttribute(outer_kernel<BQ, NPLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   Cfg::kSmemBytes));
+    DSVG_CUDA((cudaFuncSetAttribute(outer_kernel<BQ, NPLANES, BP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    Cfg::kSmemBytes)));
   }
-  const int out_tiles = ceil_div(P, 128) * ceil_div(Q, BQ);
+  const int out_tiles = ceil_div(P, BP) * ceil_div(Q, BQ);
   const int total_mblk = ceil_div(M, 64);
   int splits = sm_count() / out_tiles;  // one CTA per SM fits (shared memory): fill exactly one wave, no ragged tail
   if (splits > total_mblk / 4) splits = total_mblk / 4;       // keep >= 4 blocks of 64 rows per split
@@ -1646,7 +1708,7 @@ static int launch_outer(const CUtensorMap& a, const CUtensorMap& alo, const CUte
   const int per = ceil_div(total_mblk, splits);
   splits = ceil_div(total_mblk, per);
   dim3 grid(out_tiles, splits);
-  DSVG_CUDA(launch_k(outer_kernel<BQ, NPLANES>, grid, dim3(Cfg::kThreads), Cfg::kSmemBytes, st, a, alo, b, blo, M, P, Q, per, alpha,
+  DSVG_CUDA(launch_k(outer_kernel<BQ, NPLANES, BP>, grid, dim3(Cfg::kThreads), Cfg::kSmemBytes, st, a, alo, b, blo, M, P, Q, per, alpha,
                      alpha_dev, C, ldc, colsum_out, g_outer_lbo ? g_outer_lbo : uint32_t(Cfg::kBoxBytes),
                      g_outer_sbo ? g_outer_sbo : 1024u,
                      int(ldc % 4 == 0 && Q % 4 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0)));
@@ -1823,6 +1885,14 @@ extern "C" int dsvg_outer(const dsvg_bf16* A, size_t a_lo_off, int lda, const ds
     if (make_map(&blo, Bb + b_lo_off, Q, M, ldb, 64, 64)) return 1;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // tall 256 x 256 tiles for the path-level weight gradients (fast mode): a third less L2 -> SM traffic (see OuterCfg)
+  static const bool tall_on = [] { const char* e = getenv("DSVG_OUTER_TALL"); return !(e && e[0] == '0'); }();
+  // Measured per shape (tools/bench_outer.py, M = 131072 / 270336): 12 tall tiles 197 -> 155 us (2827 x 256) and 396 -> 291 us
+  // (1536 x 512), 4 tiles 142 -> 115 us (512 x 512), 3 tiles equal (768 x 256: 65.5 us), 2 and 1 tiles slower (51 -> 54, 39 -> 45 us):
+  // with few tiles the M range is split ~74-148 ways and the doubled reduction epilogue (256 KB of red.add per CTA) outweighs
+  // the shorter main loop.
+  if (tall_on && wide && !split && M >= 16384 && ceil_div(P, 256) * ceil_div(Q, 256) >= 4)
+    return launch_outer<256, 1, 256>(a, alo, b, blo, M, P, Q, alpha, alpha_dev, C, ldc, colsum_out, st);
   if (wide) return split ? launch_outer<256, 2>(a, alo, b, blo, M, P, Q, alpha, alpha_dev, C, ldc, colsum_out, st)
                          : launch_outer<256, 1>(a, alo, b, blo, M, P, Q, alpha, alpha_dev, C, ldc, colsum_out, st);
   return split ? launch_outer<128, 2>(a, alo, b, blo, M, P, Q, alpha, alpha_dev, C, ldc, colsum_out, st)

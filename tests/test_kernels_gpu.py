@@ -139,8 +139,17 @@ def test_linear_dropout_statistics_and_determinism():
 
 @pytest.mark.parametrize("planes", [1, 2])
 @pytest.mark.parametrize("M,P,Q", [(4096, 768, 256), (1000, 300, 200), (2048, 2827, 64), (992, 7, 256), (130, 256, 512),
-                                   (640, 100, 30), (20000, 512, 256)])   # Q % 4 != 0: scalar reductions; many row blocks
+                                   (640, 100, 30), (20000, 512, 256),    # Q % 4 != 0: scalar reductions; many row blocks
+                                   # M >= 16384: the tall 256 x 256 tiles of the big path-level weight gradients (column sums
+                                   # by the epilogue warps from shared memory)
+                                   # >= 4 such tiles (the dispatch rule): 2827 x 256, 1536 x 512 (bias sums only from the
+                                   # first Q tile), 512 x 512, ragged P with Q % 4 != 0 (scalar reductions), ragged P and Q
+                                   (16500, 2827, 256), (20000, 1536, 512), (16500, 512, 512), (17000, 1000, 250),
+                                   (33000, 600, 300),
+                                   # fewer tiles at the same row counts: the 128 x 256 tiles
+                                   (20000, 768, 256), (17000, 256, 512), (33000, 300, 200), (131072, 768, 256)])
 def test_outer_matches_fp32(planes, M, P, Q):
+    """planes = 1 runs the tall tiles where they apply; planes = 2 (parity mode) always the 128-row tiles."""
     ops = _ops()
     A, B = _rand(M, P, seed=1), _rand(M, Q, seed=2)
     lda, ldb = (P + 7) // 8 * 8, (Q + 7) // 8 * 8
