@@ -7,7 +7,9 @@
 // DeepSVG's sequences are tiny (L = 8, 31, 32, <= 66; head_dim 32/64): one warp owns one (sequence, head) pair, lane i
 // owns query row i, K/V (and Q/dO in the backward) of the pair are staged in shared memory as fp32 and read as
 // warp-broadcast float4s; the L x L probability tile never leaves shared memory.  Attention is 2.4 % of the step's
-// FLOPs; this kernel is precision-exact for both fast and parity modes.
+// FLOPs.  This file also holds the dispatcher of dsvg_attn_fwd / dsvg_attn_bwd: the tensor-core kernels of
+// attention_mma.cu take every shape of the BASELINE configs in both precision modes (one plane: attn_mma / attn_gmma,
+// two planes: attn_x3 / attn_gx3); the SIMT kernels below remain for head_dim 16, L > 80 and DSVG_ATTN=s (A/B switch).
 #include "../../include/dsvg_b200.h"
 #include <cstdlib>
 

@@ -3,8 +3,8 @@
 // 32 x 32 tile.  Q, K, V (and dO in the backward) are staged in shared memory with coalesced 16-byte loads and
 // read back with ldmatrix; scores, probabilities and all gradients of the pair stay in registers / shared memory.
 //
-//   reference: functional.py:168-248 (see attention.cu for the fp32 SIMT version used in parity mode and for
-//   shapes this kernel does not cover).  tcgen05 is not used here on purpose: a 32 x 32 x 32 problem fills 1/16 of
+//   reference: functional.py:168-248 (attention.cu keeps the fp32 SIMT version for head_dim 16 / L > 80; the parity-mode
+//   variants of these kernels -- two bf16 planes, three products -- follow further down in this file).  tcgen05 is not used here on purpose: a 32 x 32 x 32 problem fills 1/16 of
 //   the smallest UMMA tile (hard part 2); attention is 2.4 % of the step's FLOPs.
 //
 // Dropout on the probabilities uses its own element numbering (8 consecutive draws per (row, lane-in-quad)),
