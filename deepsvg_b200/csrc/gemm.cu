@@ -1555,8 +1555,11 @@ outer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
     if constexpr (BP == 256) {
       if (smem_colsum) {
-        // cross-warp reduction of the column sums through the B half of stage 0 (the transposition buffers use < 40 KB)
-        float* scr = reinterpret_cast<float*>(tiles + 40960);
+        // cross-warp reduction of the column sums through the B half of stage 0, past every warp's transposition buffer
+        constexpr int kScrOff = (Cfg::kEpiWarps * kStageWarpBytes + 1023) & ~1023;
+        static_assert(kScrOff >= Cfg::kABytes && kScrOff + Cfg::kEpiWarps * 256 * 4 <= Cfg::kStageBytes,
+                      "outer: column-sum scratch must sit in the B half of stage 0");
+        float* scr = reinterpret_cast<float*>(tiles + kScrOff);
         *reinterpret_cast<float4*>(scr + ew * 256 + lane * 8) = make_float4(cs[0], cs[1], cs[2], cs[3]);
         *reinterpret_cast<float4*>(scr + ew * 256 + lane * 8 + 4) = make_float4(cs[4], cs[5], cs[6], cs[7]);
         named_bar_sync(3, Cfg::kEpiWarps * 32);
