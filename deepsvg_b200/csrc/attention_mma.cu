@@ -406,6 +406,11 @@ __device__ __forceinline__ uint32_t pack_lo(float a, float b, uint32_t hi) {
   const float2 hf = __bfloat1622float2(h);
   return pack_bf16(a - hf.x, b - hf.y);
 }
+// acc += Xl.Yh + Xh.Yl + Xh.Yh for one n-tile (b registers i, j of the (hi, lo) B fragments): small terms first
+#define DSVG_MMA3(acc, ah, al, bh, bl, i, j)   \
+  mma_bf16(acc, al, bh[i], bh[j]);              \
+  mma_bf16(acc, ah, bl[i], bl[j]);              \
+  mma_bf16(acc, ah, bh[i], bh[j])
 // S += X . Y^T over hi/lo planes (tiles row-major [row][channel]; the lo tile follows its hi tile)
 __device__ __forceinline__ void qk_scores_x3(float (&s)[2][4][4], uint32_t x_t, uint32_t y_t, int lane) {
 #pragma unroll
@@ -428,12 +433,8 @@ __device__ __forceinline__ void qk_scores_x3(float (&s)[2][4][4], uint32_t x_t, 
       load_b_nk(bl, y_t + kTile * 2, np, ks, lane);
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
-        mma_bf16(s[mt][2 * np], al[mt], bh[0], bh[1]);
-        mma_bf16(s[mt][2 * np], ah[mt], bl[0], bl[1]);
-        mma_bf16(s[mt][2 * np], ah[mt], bh[0], bh[1]);
-        mma_bf16(s[mt][2 * np + 1], al[mt], bh[2], bh[3]);
-        mma_bf16(s[mt][2 * np + 1], ah[mt], bl[2], bl[3]);
-        mma_bf16(s[mt][2 * np + 1], ah[mt], bh[2], bh[3]);
+        DSVG_MMA3(s[mt][2 * np], ah[mt], al[mt], bh, bl, 0, 1);
+        DSVG_MMA3(s[mt][2 * np + 1], ah[mt], al[mt], bh, bl, 2, 3);
       }
     }
   }
@@ -465,12 +466,8 @@ __device__ __forceinline__ void mul_regs_kn_x3(float (&o)[2][4][4], const float 
       load_b_kn(bl, y_t + kTile * 2, np, ks, lane);
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
-        mma_bf16(o[mt][2 * np], al[mt], bh[0], bh[1]);
-        mma_bf16(o[mt][2 * np], ah[mt], bl[0], bl[1]);
-        mma_bf16(o[mt][2 * np], ah[mt], bh[0], bh[1]);
-        mma_bf16(o[mt][2 * np + 1], al[mt], bh[2], bh[3]);
-        mma_bf16(o[mt][2 * np + 1], ah[mt], bl[2], bl[3]);
-        mma_bf16(o[mt][2 * np + 1], ah[mt], bh[2], bh[3]);
+        DSVG_MMA3(o[mt][2 * np], ah[mt], al[mt], bh, bl, 0, 1);
+        DSVG_MMA3(o[mt][2 * np + 1], ah[mt], al[mt], bh, bl, 2, 3);
       }
     }
   }
@@ -497,12 +494,8 @@ __device__ __forceinline__ void mul_t_kn_x3(float (&o)[2][4][4], uint32_t z_t, u
       load_b_kn(bl, y_t + kTile * 2, np, ks, lane);
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
-        mma_bf16(o[mt][2 * np], al[mt], bh[0], bh[1]);
-        mma_bf16(o[mt][2 * np], ah[mt], bl[0], bl[1]);
-        mma_bf16(o[mt][2 * np], ah[mt], bh[0], bh[1]);
-        mma_bf16(o[mt][2 * np + 1], al[mt], bh[2], bh[3]);
-        mma_bf16(o[mt][2 * np + 1], ah[mt], bl[2], bl[3]);
-        mma_bf16(o[mt][2 * np + 1], ah[mt], bh[2], bh[3]);
+        DSVG_MMA3(o[mt][2 * np], ah[mt], al[mt], bh, bl, 0, 1);
+        DSVG_MMA3(o[mt][2 * np + 1], ah[mt], al[mt], bh, bl, 2, 3);
       }
     }
   }
@@ -1198,10 +1191,6 @@ struct GX3 {
   static constexpr int kSmemFwd = 6 * G::kTileH * 2 + G::LP;
   static constexpr int kSmemBwd = 8 * G::kTileH * 2 + 4 * G::kTileP * 2 + G::LP;
 };
-#define DSVG_MMA3(acc, ah, al, bh, bl, i, j)   \
-  mma_bf16(acc, al, bh[i], bh[j]);              \
-  mma_bf16(acc, ah, bl[i], bl[j]);              \
-  mma_bf16(acc, ah, bh[i], bh[j])
 
 template <int HD, int NT>
 __device__ __forceinline__ void gx3_scores(float (&s)[2 * NT][4], uint32_t x_tile, uint32_t y_tile, int w, int lane) {
