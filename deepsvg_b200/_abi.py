@@ -13,12 +13,13 @@ U64 = C.c_uint64
 DROP = [F, U32, U64]
 
 #: must equal dsvg_abi_version() of the loaded library (checked in _lib.load())
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 SIGNATURES = {
     "dsvg_abi_version": (I, []),
     "dsvg_linear": (I, [P, Z, I, P, Z, I, I, I, I, P, P]),
     "dsvg_outer": (I, [P, Z, I, P, Z, I, I, I, I, F, P, P, I, P, P]),
+    "dsvg_outer_group": (I, [I, P, I, P]),
     "dsvg_linear_ln_fusable": (I, [I, I, I]),
     "dsvg_linear_ln_fwd": (I, [P, Z, I, P, Z, I, I, I, I, P, P, P, P, P, P, P]),
     "dsvg_linear_ln_bwd": (I, [P, Z, I, P, Z, I, I, I, I, P, P, P, P, P, P, P] + DROP + [P, P, P]),

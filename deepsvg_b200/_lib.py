@@ -41,6 +41,23 @@ class Epilogue(C.Structure):
     ]
 
 
+class OuterProblem(C.Structure):
+    """Mirror of `dsvg_outer_problem` (include/dsvg_b200.h)."""
+    _fields_ = [
+        ("A", C.c_void_p),
+        ("lda", C.c_int),
+        ("B", C.c_void_p),
+        ("ldb", C.c_int),
+        ("P", C.c_int),
+        ("Q", C.c_int),
+        ("alpha", C.c_float),
+        ("alpha_dev", C.c_void_p),
+        ("C", C.c_void_p),
+        ("ldc", C.c_int),
+        ("colsum_out", C.c_void_p),
+    ]
+
+
 def lib_path():
     return _LIB_PATH
 

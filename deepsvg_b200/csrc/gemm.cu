@@ -1368,19 +1368,20 @@ struct OuterCfg {
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kOnesBytes + kStagingBytes + 256;
 };
 
-template <int BQ, int NPLANES, int BP = 128>
-__global__ void __launch_bounds__((OuterCfg<BQ, NPLANES, BP>::kThreads), 1)
-outer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
-             const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo, int M, int P, int Q,
-             int mblk_per_split, float alpha, const float* alpha_dev, float* C, int ldc, float* colsum_out,
-             uint32_t lbo, uint32_t sbo, int vec) {
+// The whole CTA program; `tile_id` / `split_id` select the output tile and the M range (the block indices of the single-problem
+// kernel, a table lookup in the grouped one).  The tensor maps live in kernel-parameter space (__grid_constant__) of the caller.
+template <int BQ, int NPLANES, int BP>
+__device__ __forceinline__ void outer_body(const CUtensorMap* tmA_p, const CUtensorMap* tmAlo_p, const CUtensorMap* tmB_p,
+                                           const CUtensorMap* tmBlo_p, int M, int P, int Q, int mblk_per_split, float alpha,
+                                           const float* alpha_dev, float* C, int ldc, float* colsum_out, uint32_t lbo,
+                                           uint32_t sbo, int vec, int tile_id, int split_id) {
   using Cfg = OuterCfg<BQ, NPLANES, BP>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* tiles = smem;
   uint8_t* ones = smem + Cfg::kStages * Cfg::kStageBytes;  // 1024-aligned
   const int q_tiles = (Q + BQ - 1) / BQ;
-  const bool do_colsum = colsum_out != nullptr && (blockIdx.x % q_tiles) == 0;
+  const bool do_colsum = colsum_out != nullptr && (tile_id % q_tiles) == 0;
   // tall tiles: the epilogue warps read every A stage too (column sums) and release it together with the MMA commit
   const bool smem_colsum = BP == 256 && do_colsum;
   float* staging = reinterpret_cast<float*>(tiles);   // epilogue only, after the main loop (see OuterCfg)
@@ -1394,8 +1395,8 @@ outer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(tmA_p);
+    tma_prefetch_desc(tmB_p);
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], smem_colsum ? 1 + Cfg::kEpiWarps : 1);
@@ -1417,10 +1418,10 @@ outer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();   // everything above touched only this CTA's shared memory / TMEM
 
-  const int p0 = (blockIdx.x / q_tiles) * BP;
-  const int q0 = (blockIdx.x % q_tiles) * BQ;
+  const int p0 = (tile_id / q_tiles) * BP;
+  const int q0 = (tile_id % q_tiles) * BQ;
   const int total_mblk = (M + 63) / 64;
-  const int mb_begin = blockIdx.y * mblk_per_split;
+  const int mb_begin = split_id * mblk_per_split;
   const int mb_end = min(total_mblk, mb_begin + mblk_per_split);
   const int num_mb = mb_end - mb_begin;  // >= 1 by construction of the grid
 
@@ -1433,18 +1434,18 @@ outer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         uint8_t* st = tiles + stage * Cfg::kStageBytes;
         mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
 #pragma unroll
-        for (int i = 0; i < BP / 64; ++i) tma_load_2d(st + i * Cfg::kBoxBytes, &tmA, &full_bar[stage], p0 + 64 * i, mb * 64);
+        for (int i = 0; i < BP / 64; ++i) tma_load_2d(st + i * Cfg::kBoxBytes, tmA_p, &full_bar[stage], p0 + 64 * i, mb * 64);
 #pragma unroll
         for (int j = 0; j < BQ / 64; ++j)
-          tma_load_2d(st + Cfg::kABytes + j * Cfg::kBoxBytes, &tmB, &full_bar[stage], q0 + 64 * j, mb * 64);
+          tma_load_2d(st + Cfg::kABytes + j * Cfg::kBoxBytes, tmB_p, &full_bar[stage], q0 + 64 * j, mb * 64);
         if (NPLANES == 2) {
           uint8_t* lo = st + Cfg::kABytes + Cfg::kBBytes;
 #pragma unroll
           for (int i = 0; i < 2; ++i)
-            tma_load_2d(lo + i * Cfg::kBoxBytes, &tmAlo, &full_bar[stage], p0 + 64 * i, mb * 64);
+            tma_load_2d(lo + i * Cfg::kBoxBytes, tmAlo_p, &full_bar[stage], p0 + 64 * i, mb * 64);
 #pragma unroll
           for (int j = 0; j < BQ / 64; ++j)
-            tma_load_2d(lo + Cfg::kABytes + j * Cfg::kBoxBytes, &tmBlo, &full_bar[stage], q0 + 64 * j, mb * 64);
+            tma_load_2d(lo + Cfg::kABytes + j * Cfg::kBoxBytes, tmBlo_p, &full_bar[stage], q0 + 64 * j, mb * 64);
         }
       }
       __syncwarp();
@@ -1588,6 +1589,41 @@ outer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
 }
 
+template <int BQ, int NPLANES, int BP = 128>
+__global__ void __launch_bounds__((OuterCfg<BQ, NPLANES, BP>::kThreads), 1)
+outer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
+             const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo, int M, int P, int Q,
+             int mblk_per_split, float alpha, const float* alpha_dev, float* C, int ldc, float* colsum_out,
+             uint32_t lbo, uint32_t sbo, int vec) {
+  outer_body<BQ, NPLANES, BP>(&tmA, &tmAlo, &tmB, &tmBlo, M, P, Q, mblk_per_split, alpha, alpha_dev, C, ldc, colsum_out, lbo, sbo,
+                              vec, int(blockIdx.x), int(blockIdx.y));
+}
+
+// Grouped launch: the weight gradients of one transformer block (QKV, out-proj, FFN1, FFN2: same row count M, different
+// operands) share ONE wave of CTAs.  Launched one by one, each of them splits its M range 24-74 ways to fill the machine and pays
+// 19 MB of red.add traffic and a pipeline ramp per launch for 0.25-0.8 MB of result; together they have 8 tall tiles, the M
+// range is split ~18 ways, and every CTA streams >100 row blocks.  Tall 256 x 256 tiles throughout (see OuterCfg).
+constexpr int kMaxGroup = 4;
+struct OuterGroup {
+  CUtensorMap a[kMaxGroup];
+  CUtensorMap b[kMaxGroup];
+  float* C[kMaxGroup];
+  float* colsum[kMaxGroup];
+  const float* alpha_dev[kMaxGroup];
+  float alpha[kMaxGroup];
+  int P[kMaxGroup], Q[kMaxGroup], ldc[kMaxGroup], vec[kMaxGroup];
+  int cta_begin[kMaxGroup + 1];   // first CTA of each problem (tiles x splits CTAs per problem)
+  int n, M, splits, mblk_per_split;
+};
+__global__ void __launch_bounds__((OuterCfg<256, 1, 256>::kThreads), 1)
+outer_group_kernel(const __grid_constant__ OuterGroup g, uint32_t lbo, uint32_t sbo) {
+  int p = 0;
+  while (p + 1 < g.n && int(blockIdx.x) >= g.cta_begin[p + 1]) ++p;
+  const int local = int(blockIdx.x) - g.cta_begin[p];
+  outer_body<256, 1, 256>(&g.a[p], &g.a[p], &g.b[p], &g.b[p], g.M, g.P[p], g.Q[p], g.mblk_per_split, g.alpha[p], g.alpha_dev[p],
+                          g.C[p], g.ldc[p], g.colsum[p], lbo, sbo, g.vec[p], local / g.splits, local % g.splits);
+}
+
 static int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -1724,7 +1760,7 @@ static int launch_outer(const CUtensorMap& a, const CUtensorMap& alo, const CUte
 using namespace dsvg;
 
 extern "C" const char* dsvg_last_error(void) { return dsvg::last_error(); }
-extern "C" int dsvg_abi_version(void) { return 4; }
+extern "C" int dsvg_abi_version(void) { return 5; }
 extern "C" void dsvg_debug_outer_desc(unsigned lbo, unsigned sbo) {
   dsvg::g_outer_lbo = lbo;
   dsvg::g_outer_sbo = sbo;
@@ -1864,6 +1900,47 @@ extern "C" int dsvg_linear_ln_bwd(const dsvg_bf16* dY, size_t dy_lo_off, int lda
   if (make_map(&a, reinterpret_cast<const bf16*>(dY), K, M, lda, 64, 128)) return 1;
   if (make_map(&b, reinterpret_cast<const bf16*>(W), K, N, ldb, 64, 256)) return 1;
   return launch_linear_mode<256, 1, 9>(a, a, b, b, M, N, K, ep, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int dsvg_outer_group(int n, const dsvg_outer_problem* pr, int M, void* stream) {
+  DSVG_CHECK(n >= 1 && n <= kMaxGroup && pr != nullptr && M > 0, "dsvg_outer_group: 1..%d problems", kMaxGroup);
+  OuterGroup g{};
+  g.n = n;
+  g.M = M;
+  int tiles_total = 0, tiles[kMaxGroup];
+  for (int i = 0; i < n; ++i) {
+    const dsvg_outer_problem& q = pr[i];
+    DSVG_CHECK(q.A && q.B && q.C && q.P > 0 && q.Q > 0, "dsvg_outer_group: bad problem %d", i);
+    DSVG_CHECK(q.lda % 8 == 0 && q.ldb % 8 == 0, "dsvg_outer_group: lda/ldb must be multiples of 8");
+    if (make_map(&g.a[i], reinterpret_cast<const bf16*>(q.A), q.P, M, q.lda, 64, 64)) return 1;
+    if (make_map(&g.b[i], reinterpret_cast<const bf16*>(q.B), q.Q, M, q.ldb, 64, 64)) return 1;
+    g.C[i] = q.C; g.colsum[i] = q.colsum_out; g.alpha_dev[i] = q.alpha_dev; g.alpha[i] = q.alpha;
+    g.P[i] = q.P; g.Q[i] = q.Q; g.ldc[i] = q.ldc;
+    g.vec[i] = int(q.ldc % 4 == 0 && q.Q % 4 == 0 && (reinterpret_cast<uintptr_t>(q.C) & 15) == 0);
+    tiles[i] = ceil_div(q.P, 256) * ceil_div(q.Q, 256);
+    tiles_total += tiles[i];
+  }
+  const int total_mblk = ceil_div(M, 64);
+  int splits = sm_count() / tiles_total;
+  if (splits > total_mblk / 4) splits = total_mblk / 4;
+  if (splits < 1) splits = 1;
+  const int per = ceil_div(total_mblk, splits);
+  splits = ceil_div(total_mblk, per);
+  g.splits = splits;
+  g.mblk_per_split = per;
+  g.cta_begin[0] = 0;
+  for (int i = 0; i < n; ++i) g.cta_begin[i + 1] = g.cta_begin[i] + tiles[i] * splits;
+  for (int i = n; i < kMaxGroup; ++i) g.cta_begin[i + 1] = g.cta_begin[n];
+  using Cfg = OuterCfg<256, 1, 256>;
+  static bool configured[kMaxDevices] = {};
+  if (first_use_on_device(configured)) {
+    DSVG_CUDA(cudaFuncSetAttribute(outer_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+  }
+  DSVG_CUDA(launch_k(outer_group_kernel, dim3(g.cta_begin[n]), dim3(Cfg::kThreads), Cfg::kSmemBytes,
+                     static_cast<cudaStream_t>(stream), g, g_outer_lbo ? g_outer_lbo : uint32_t(Cfg::kBoxBytes),
+                     g_outer_sbo ? g_outer_sbo : 1024u));
+  ++g_launches;
+  return 0;
 }
 
 extern "C" int dsvg_outer(const dsvg_bf16* A, size_t a_lo_off, int lda, const dsvg_bf16* B, size_t b_lo_off, int ldb,

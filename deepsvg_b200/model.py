@@ -283,6 +283,7 @@ class SVGTransformer(nn.Module):
         self._sites = {}
         self._wcache = {}
         self._eps_override = None      # tests inject the VAE noise here (SURVEY.md 8c hazard 2)
+        self.wgrad_group = os.environ.get("DSVG_WGRAD_GROUP", "1") != "0"   # one weight-gradient launch per block
 
     # -------------------------------------------------------------------------------------------------
     def _param(self, name):
@@ -910,12 +911,26 @@ class SVGTransformer(nn.Module):
         P = lambda n: self._param(pre + "." + n)
         G = lambda n: gd[pre + "." + n]
         pff = self._drop(sv, pre + ".dropff")
+        # The block's four weight gradients: one grouped launch at the end of the block for the path-level row counts in fast
+        # mode (ops.outer_group: they then share one wave of CTAs), separate launches otherwise.
+        # Measured (hier, d_model 256: 8 tall tiles per block): `outer` family 2.57 -> 2.14 ms per step, step 12.93 -> 12.69 ms.  With
+        # d_model 512 the block has 24 tiles, each launch already fills the machine with few splits, and grouping changes nothing
+        # (12.0 vs 12.2 ms): those stay separate launches.
+        t256 = lambda n: (n + 255) // 256
+        n_tiles = t256(3 * d) * t256(d) + t256(d) * t256(d) + 2 * t256(ff) * t256(d)
+        grouped = [] if (pl == 1 and M >= 16384 and self.wgrad_group and n_tiles <= 16) else None
+
+        def wgrad(A, B, P_, Q_, w, b):
+            if grouped is None:
+                ops.outer(A, B, M, P_, Q_, w, colsum=b)
+            else:
+                grouped.append((A, B, P_, Q_, w, b))
         # ---- FFN ----
-        ops.outer(dx2_act, s["h"], M, d, ff, G("linear2.weight"), colsum=G("linear2.bias"))
+        wgrad(dx2_act, s["h"], d, ff, G("linear2.weight"), G("linear2.bias"))
         dh = Act(M, ff, pl, dev)
         _, w2t = self._pack(pre + ".linear2.weight")
         ops.linear(dx2_act, w2t, M, ff, d, mask=s["h"], mask_scale=1.0 / (1.0 - pff[0]) if pff[0] > 0 else 1.0, out_act=dh)
-        ops.outer(dh, s["b"], M, ff, d, G("linear1.weight"), colsum=G("linear1.bias"))
+        wgrad(dh, s["b"], ff, d, G("linear1.weight"), G("linear1.bias"))
         # The fused dgrad + LayerNorm-backward kernel (dsvg_linear_ln_bwd) is correct (tests/test_kernels_gpu.py) but measured
         # SLOWER than the two kernels it replaces (171 vs 147 us at M = 131072, K = 512: its two-pass epilogue is
         # latency-bound at 18 warps per SM, profiles/README.md), so it is opt-in: DSVG_LN_FUSE_BWD=1.
@@ -932,14 +947,14 @@ class SVGTransformer(nn.Module):
             ops.ln_bwd(s["x1"], s["mean2"], s["rstd2"], P("norm2.weight"), M, d, dy=db, dx_in=dx2, dx_out=dx1, dact=dt,
                        drop=self._drop(sv, pre + ".drop1"), dgamma=G("norm2.weight"), dbeta=G("norm2.bias"))
         # ---- attention ----
-        ops.outer(dt, s["o"], M, d, d, G("self_attn.out_proj.weight"), colsum=G("self_attn.out_proj.bias"))
+        wgrad(dt, s["o"], d, d, G("self_attn.out_proj.weight"), G("self_attn.out_proj.bias"))
         do = Act(M, d, pl, dev)
         _, wot = self._pack(pre + ".self_attn.out_proj.weight")
         ops.linear(dt, wot, M, d, d, out_act=do)
         dqkv = Act(M, 3 * d, pl, dev)
         ops.attn_bwd(s["qkv"], key_valid, do, dqkv, nseq, L, H, hd, float(hd) ** -0.5, self._drop(sv, pre + ".attn"),
                      causal=pre.startswith(getattr(sv, "causal_stack", "\0")))
-        ops.outer(dqkv, s["a"], M, 3 * d, d, G("self_attn.in_proj_weight"), colsum=G("self_attn.in_proj_bias"))
+        wgrad(dqkv, s["a"], 3 * d, d, G("self_attn.in_proj_weight"), G("self_attn.in_proj_bias"))
         _, wit = self._pack(pre + ".self_attn.in_proj_weight")
         dx0 = torch.empty(M, d, device=dev)
         dx0_act = Act(M, d, pl, dev) if want_dact else None
@@ -951,6 +966,8 @@ class SVGTransformer(nn.Module):
             ops.linear(dqkv, wit, M, d, 3 * d, out_act=da)
             ops.ln_bwd(s["x"], s["mean1"], s["rstd1"], P("norm1.weight"), M, d, dy=da, dx_in=dx1, dx_out=dx0, dact=dx0_act,
                        drop=prev_drop, dgamma=G("norm1.weight"), dbeta=G("norm1.bias"))
+        if grouped:
+            ops.outer_group(grouped, M)
         return dx0, dx0_act, dx1
 
     def _globals_bwd(self, sv, gd, pre, dx1, n_groups, L, zmem, dzmem, lab, dlab, lab_rows_per_group, lab_rpg):

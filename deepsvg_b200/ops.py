@@ -139,6 +139,24 @@ def outer(A, B, M, P, Q, Cout, *, alpha=1.0, alpha_dev=None, colsum=None):
     _lib.check(rc, "dsvg_outer")
 
 
+def outer_group(problems, M):
+    """problems: list of (A, B, P, Q, Cout, colsum) with single-plane Act operands sharing the row count M (the weight gradients
+    of one transformer block): Cout += A^T . B and colsum += column sums of A for each, in ONE launch (dsvg_outer_group)."""
+    n = len(problems)
+    arr = (_lib.OuterProblem * n)()
+    flops = nbytes = 0.0
+    for i, (A, B, P, Q, Cout, colsum) in enumerate(problems):
+        assert A.planes == 1 and B.planes == 1
+        arr[i].A, arr[i].lda, arr[i].B, arr[i].ldb = A.ptr, A.ld, B.ptr, B.ld
+        arr[i].P, arr[i].Q, arr[i].alpha, arr[i].alpha_dev = P, Q, 1.0, None
+        arr[i].C, arr[i].ldc, arr[i].colsum_out = Cout.data_ptr(), Cout.stride(0), _p(colsum) or None
+        flops += 2.0 * M * P * Q
+        nbytes += 2.0 * M * (P + Q) + 4.0 * P * Q
+    with _Prof("outer", flops, None, nbytes):
+        rc = _lib.load().dsvg_outer_group(n, C.cast(arr, C.c_void_p), M, _stream())
+    _lib.check(rc, "dsvg_outer_group")
+
+
 def seq_prep(commands, nseq, L, first_eos, visible, key_valid, grp, counts):
     rc = _lib.load().dsvg_seq_prep(commands.data_ptr(), nseq, L, _p(first_eos), _p(visible), _p(key_valid), _p(grp),
                                    _p(counts), _stream())

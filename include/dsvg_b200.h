@@ -83,6 +83,24 @@ int dsvg_linear(const dsvg_bf16* X, size_t x_lo_off, int lda, const dsvg_bf16* W
 int dsvg_outer(const dsvg_bf16* A, size_t a_lo_off, int lda, const dsvg_bf16* B, size_t b_lo_off, int ldb, int M,
                int P, int Q, float alpha, const float* alpha_dev, float* C, int ldc, float* colsum_out, void* stream);
 
+/* Several weight gradients with the SAME row count M in one launch (single-plane operands, path-level row counts): the four
+ * Linear layers of one transformer block (in_proj, out_proj, linear1, linear2: improved_transformer.py:43-53, gradients taken by
+ * loss.backward() at train.py:98).  Semantics per problem as dsvg_outer; the problems share one wave of CTAs, so the M range is
+ * split ~4x less finely than when each is launched alone (less fp32 atomic traffic, longer streaming loops per CTA). */
+typedef struct dsvg_outer_problem {
+  const dsvg_bf16* A; /* [M, P], row stride lda */
+  int lda;
+  const dsvg_bf16* B; /* [M, Q], row stride ldb */
+  int ldb;
+  int P, Q;
+  float alpha;
+  const float* alpha_dev; /* optional device scalar */
+  float* C;               /* [P, Q] fp32 accumulator, row stride ldc */
+  int ldc;
+  float* colsum_out;      /* optional [P] */
+} dsvg_outer_problem;
+int dsvg_outer_group(int n_problems, const dsvg_outer_problem* problems, int M, void* stream);
+
 /* GEMM + LayerNorm in one kernel (fast mode).  When the CTA tile of dsvg_linear owns whole rows (N = d_model = 256,
  * path-level row counts, single-plane operands: ask dsvg_linear_ln_fusable) the LayerNorm that follows a residual-stream
  * linear, and the LayerNorm backward that follows the input-gradient GEMM of the layer's QKV / FFN1 linear, run in that

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     assert len(fns) >= 28
     for name in fns:
         assert hasattr(lib, name), name
-    assert lib.dsvg_abi_version() == 4
+    assert lib.dsvg_abi_version() == 5
     assert lib.dsvg_launch_count() == 0          # nothing launched: loading needs no GPU
 
 
@@ -43,6 +43,19 @@ def test_epilogue_struct_matches_header():
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     names = [re.split(r"[\s\*]+", f.strip())[-1] for f in body.split(";") if f.strip()]
     assert names == [f[0] for f in Epilogue._fields_]
+
+
+def test_outer_problem_struct_matches_header():
+    from deepsvg_b200._lib import OuterProblem
+    hdr = open(os.path.join(ROOT, "include", "dsvg_b200.h")).read()
+    body = re.search(r"typedef struct dsvg_outer_problem \{(.*?)\} dsvg_outer_problem;", hdr, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for f in body.split(";"):
+        f = f.strip()
+        if f:
+            names += [re.split(r"[\s\*]+", part.strip())[-1] for part in f.split(",")]
+    assert names == [f[0] for f in OuterProblem._fields_]
 
 
 def test_calls_fail_loudly_without_gpu():

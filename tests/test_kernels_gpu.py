@@ -165,6 +165,27 @@ def test_outer_matches_fp32(planes, M, P, Q):
         assert _rel(Cout, (A.double().t() @ B.double()).float() + 1.0) < 3e-5
 
 
+@pytest.mark.parametrize("M,d,ff", [(20000, 256, 512), (131072, 256, 512), (16500, 128, 256), (17000, 512, 512), (16400, 200, 300)])
+def test_outer_group_matches_fp32(M, d, ff):
+    """dsvg_outer_group: the four weight gradients of one block (in_proj, out_proj, linear1, linear2) in one launch, every
+    problem with its bias column sums, accumulating into non-zero buffers; ragged tile edges at d = 128 / 200."""
+    ops = _ops()
+    shapes = [(3 * d, d), (d, d), (ff, d), (d, ff)]
+    probs, refs = [], []
+    for i, (P, Q) in enumerate(shapes):
+        A, B = _rand(M, P, seed=10 + i), _rand(M, Q, seed=20 + i)
+        aa = ops.act_from_float(A, 1, ld=(P + 7) // 8 * 8)
+        ba = ops.act_from_float(B, 1, ld=(Q + 7) // 8 * 8)
+        Cout = torch.full((P, Q), 0.5, device=DEV)
+        cs = torch.full((P,), -1.0, device=DEV)
+        probs.append((aa, ba, P, Q, Cout, cs))
+        refs.append(((aa.float().double().t() @ ba.float().double()).float() + 0.5, aa.float().double().sum(0).float() - 1.0))
+    ops.outer_group(probs, M)
+    for (aa, ba, P, Q, Cout, cs), (rc, rs) in zip(probs, refs):
+        assert _rel(Cout, rc) < 2e-5, (P, Q)
+        assert _rel(cs, rs) < 2e-5, (P, Q)
+
+
 # ------------------------------------------------------------------------------------------------ LayerNorm
 @pytest.mark.parametrize("D", [128, 256, 512])
 def test_layernorm_fwd_bwd(D):
